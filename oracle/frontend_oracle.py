@@ -1,0 +1,480 @@
+"""CPU oracle for the per-clip audio front-end  --  TEST INFRASTRUCTURE ONLY.
+
+This module is the *checker*, never the product.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it.  The shipped path (``audio-training_b200``) never does and fails
+loudly when its CUDA library is missing.
+
+It restates, in numpy, the arithmetic of TheCacophonyProject/audio-training's feature
+path.  Every function cites the reference file:line it follows (paths relative to
+``/root/reference``).  The reference's numerical kernels live in un-vendored,
+un-pinned third-party wheels (``requirements.txt:1-13`` lists tensorflow, librosa, ...
+without versions); their documented semantics are restated here:
+
+* ``tf.signal.frame`` / ``hann_window`` / ``stft``    (TensorFlow, version un-pinned)
+* ``librosa.stft`` (center=True, periodic Hann, FFT evaluated in f64, cast to c64)
+* ``tf.scan`` (sequential left fold, first output = fn(initializer, elems[0]))
+
+PARITY PINNING.  The reference ships no tests and no golden vectors.
+What pins this oracle instead (``oracle/ref_shim/gen_golden.py``, fixtures committed
+under ``tests/golden/``):
+  * ``custommel.py`` is executed *itself* (its one librosa call, ``fft_frequencies``,
+    is ``np.fft.rfftfreq``) -> filterbank goldens are real reference outputs;
+  * ``predict_utils.py`` is executed itself for ``normalize_data`` and the integer
+    window arithmetic of ``load_samples``;
+  * ``tfpcen.py``, and the feature functions of ``tfdataset.py`` / ``badwinner2.py``
+    are executed from their own source over a numpy stand-in for the ``tf`` namespace,
+    which pins operation order and constants at the Python level.
+The TensorFlow/librosa *internals* (framing, window, FFT, scan) remain restated from
+documentation: for those, parity is UNPINNED and says so in DESIGN.md.
+
+Two arithmetic modes:
+  dtype=np.float64 : ground truth the CUDA path is compared against with the north-star
+                     tolerance |ours - oracle| <= 1e-4*|oracle| + 1e-5;
+  dtype=np.float32 : follows the reference's own rounding order (what TF/numpy do).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+try:  # scipy's pocketfft keeps float32 in float32 (like TF's CPU FFT)
+    import scipy.fft as _sfft
+except Exception:  # pragma: no cover
+    _sfft = None
+
+SR = 48000
+CLIP_SAMPLES = 144000
+N_FFT = 4096
+HOP = 281
+N_MELS = 160
+BREAK_FREQ = 1000
+FMIN = 100
+FMAX = 11000
+
+REL_TOL = 1e-4  # north star
+ABS_TOL = 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# a4  custom mel filterbank                                       custommel.py:6-54
+# --------------------------------------------------------------------------------------
+def hz_to_mel(frequencies, break_freq):
+    """custommel.py:6-8  mel = 2595 * log10(1 + f / break)."""
+    return 2595.0 * np.log10(1.0 + np.asarray(frequencies, dtype=np.float64) / break_freq)
+
+
+def mel_frequencies(n_mels, fmin, fmax, break_freq):
+    """custommel.py:11-15  n_mels points uniformly spaced on the mel axis, back in Hz."""
+    lo, hi = hz_to_mel(fmin, break_freq), hz_to_mel(fmax, break_freq)
+    return break_freq * (10.0 ** (np.linspace(lo, hi, n_mels) / 2595.0) - 1.0)
+
+
+def mel_f(sr, n_mels, fmin, fmax, n_fft, break_freq):
+    """custommel.py:18-54  triangular filters, Slaney area normalisation, stored as f32.
+
+    ``librosa.fft_frequencies`` (custommel.py:24) is ``np.fft.rfftfreq(n_fft, 1/sr)``.
+    The f32 rounding happens when the f64 triangle is stored into the f32 weight array
+    (custommel.py:21,37) and again when the f32 row is scaled by the f64 ``enorm``
+    (in-place multiply of an f32 array, custommel.py:42).
+    """
+    n_mels = int(n_mels)
+    n_bins = int(1 + n_fft // 2)
+    bin_hz = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    edges = mel_frequencies(n_mels + 2, fmin, fmax, break_freq)
+    width = np.diff(edges)
+    delta = edges[:, None] - bin_hz[None, :]  # ramps, custommel.py:29
+    rising = -delta[:-2] / width[:-1, None]
+    falling = delta[2:] / width[1:, None]
+    tri = np.maximum(0, np.minimum(rising, falling)).astype(np.float32)
+    assert tri.shape == (n_mels, n_bins)
+    area = 2.0 / (edges[2 : n_mels + 2] - edges[:n_mels])
+    tri *= area[:, None]  # in-place: f32 * f64 -> rounded to f32, like the reference
+    return tri
+
+
+# --------------------------------------------------------------------------------------
+# a1  per-clip normalisation        tfdataset.py:1916-1934, predict_utils.py:153-160
+# --------------------------------------------------------------------------------------
+def normalize(x, dtype=np.float32):
+    """x-=min; x = x/max(x) + 1e-6; x = (x-0.5)*2   over the last axis (Q1: +1e-6 is
+    added after the divide).  A constant clip gives 0/0 = NaN like the reference."""
+    x = np.asarray(x, dtype=dtype)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        x = x - np.min(x, axis=-1, keepdims=True)
+        x = x / np.max(x, axis=-1, keepdims=True) + dtype(0.000001)
+        x = x - dtype(0.5)
+        x = x * dtype(2)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# a2  framing / window / rFFT
+# --------------------------------------------------------------------------------------
+def num_frames_tf(n, frame_length, step, pad_end):
+    """tf.signal.frame: pad_end -> ceil(n/step); else 1 + (n - L)//step (0 if n < L)."""
+    if pad_end:
+        return -(-n // step)
+    return 0 if n < frame_length else 1 + (n - frame_length) // step
+
+
+def num_frames_center(n, hop):
+    """librosa.stft(center=True): 1 + n // hop."""
+    return 1 + n // hop
+
+
+def hann_periodic(length, dtype=np.float64):
+    """tf.signal.hann_window(periodic=True) == scipy get_window('hann', fftbins=True):
+    0.5 - 0.5 cos(2 pi n / L) for even L."""
+    n = np.arange(length, dtype=np.float64)
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * n / length)).astype(dtype)
+
+
+def frame_tf(x, frame_length, step, pad_end=True):
+    """tf.signal.frame(x, L, S, pad_end, pad_value=0) on the last axis (tfdataset.py:2026-2034
+    passes pad_end=True; raw_to_mel_dual, tfdataset.py:1824-1832, does not)."""
+    x = np.asarray(x)
+    n = x.shape[-1]
+    t = num_frames_tf(n, frame_length, step, pad_end)
+    if pad_end:
+        need = max(0, frame_length + step * (t - 1) - n)
+        x = np.concatenate([x, np.zeros(x.shape[:-1] + (need,), dtype=x.dtype)], axis=-1)
+    idx = step * np.arange(t)[:, None] + np.arange(frame_length)[None, :]
+    return x[..., idx]
+
+
+def frame_center(x, n_fft, hop, pad_mode="constant"):
+    """librosa.stft centred framing (predict_utils.py:194, audiodataset.py:1303): pad n_fft//2
+    on both sides (zeros for librosa >= 0.10, reflect before), frame t covers
+    [hop*t - n_fft/2, hop*t + n_fft/2)."""
+    x = np.asarray(x)
+    half = n_fft // 2
+    pad = [(0, 0)] * (x.ndim - 1) + [(half, half)]
+    xp = np.pad(x, pad, mode=pad_mode)
+    t = num_frames_center(x.shape[-1], hop)
+    idx = hop * np.arange(t)[:, None] + np.arange(n_fft)[None, :]
+    return xp[..., idx]
+
+
+def _rfft(frames, dtype):
+    if dtype == np.float32 and _sfft is not None:
+        return _sfft.rfft(frames.astype(np.float32), axis=-1)
+    out = np.fft.rfft(frames.astype(np.float64), axis=-1)
+    return out.astype(np.complex64) if dtype == np.float32 else out
+
+
+def stft_tf(x, frame_length=N_FFT, step=HOP, pad_end=True, dtype=np.float64):
+    """tf.signal.stft(x, L, S, fft_length=L, window_fn=hann_window, pad_end) ->
+    [..., T, L/2+1]  (tfdataset.py:2026-2034).  f32 mode: window in f32, multiply in f32,
+    rfft in f32 -> complex64."""
+    frames = frame_tf(np.asarray(x, dtype=dtype), frame_length, step, pad_end)
+    win = hann_periodic(frame_length, dtype)
+    return _rfft(frames * win, dtype)
+
+
+def stft_librosa(x, n_fft=N_FFT, hop=HOP, pad_mode="constant", dtype=np.float64):
+    """librosa.stft(y, n_fft, hop_length) -> [..., n_fft/2+1, T].  The f64 window times the f32
+    frames is an f64 FFT whose result is stored as complex64 (f32 mode) -- librosa does this
+    for f32 input."""
+    frames = frame_center(np.asarray(x, dtype=dtype), n_fft, hop, pad_mode)
+    win = hann_periodic(n_fft, np.float64)
+    z = np.fft.rfft(frames.astype(np.float64) * win, axis=-1)
+    if dtype == np.float32:
+        z = z.astype(np.complex64)
+    return np.swapaxes(z, -1, -2)
+
+
+# --------------------------------------------------------------------------------------
+# a3 + a5 + a6  power, mel projection, channel repeat            tfdataset.py:2007-2059
+# --------------------------------------------------------------------------------------
+def raw_to_mel(x, weights=None, n_fft=N_FFT, hop=HOP, pad_end=True, channels=3, power=2,
+               dtype=np.float64):
+    """Path A: stft -> pow(z,2) -> transpose -> abs -> batch_dot(W, .) -> expand+repeat(3).
+
+    tfdataset.py:2026-2053.  `abs(z**2)` (Q3) is |z|^2; f32 mode evaluates it the reference's
+    way on complex64.  raw_to_mel_dual (tfdataset.py:1834-1835) takes abs only: power=1.
+    Returns [B, n_mels, T, channels] (channels=0 -> no channel axis)."""
+    if weights is None:
+        weights = mel_f(SR, N_MELS, FMIN, FMAX, n_fft, BREAK_FREQ)
+    x = np.asarray(x, dtype=dtype)
+    single = x.ndim == 1
+    if single:
+        x = x[None]
+    z = stft_tf(x, n_fft, hop, pad_end, dtype)
+    if power == 2:
+        p = np.abs(z ** 2) if dtype == np.float32 else (z.real ** 2 + z.imag ** 2)
+    else:
+        p = np.abs(z)
+    p = np.swapaxes(p, 1, 2)  # [B, K, T]
+    img = np.matmul(weights.astype(dtype)[None], p.astype(dtype))
+    if channels:
+        img = np.repeat(img[..., None], channels, axis=3)
+    return img[0] if single else img
+
+
+def mel_spec(stft, sr, n_fft, hop_length, n_mels, fmin, fmax, break_freq=1750, power=2,
+             dtype=np.float64):
+    """custommel.py:57-61  |stft|**power then filterbank . magnitude (Q8: bank rebuilt per call,
+    default break 1750)."""
+    mag = np.abs(stft).astype(dtype) ** power
+    return mel_f(sr, n_mels, fmin, fmax, n_fft, break_freq).astype(dtype).dot(mag)
+
+
+def get_spect(data, sr=SR, hop_length=HOP, mel_break=BREAK_FREQ, n_mels=N_MELS, fmin=FMIN,
+              fmax=FMAX, n_fft=N_FFT, power=2, db_scale=False, channels=1,
+              pad_mode="constant", dtype=np.float64):
+    """Path B, default branch htk=True of predict_utils.py:163-239 (:190-215).  Q9: the fmax
+    argument is `11000 if fmin is None else fmax`."""
+    spec = np.abs(stft_librosa(data, n_fft, hop_length, pad_mode, dtype))
+    mel = mel_spec(spec, sr, n_fft, hop_length, n_mels, 100 if fmin is None else fmin,
+                   11000 if fmin is None else fmax, mel_break, power, dtype)
+    if db_scale:
+        mel = librosa_power_to_db(mel)
+    mel = mel[..., None]
+    if channels > 1:
+        mel = np.repeat(mel, channels, axis=2)
+    return mel
+
+
+def mel_from_spectrogram(spec, weights=None, power=1, dtype=np.float64):
+    """Path C, tfdataset.py:1082-1099: reshape(2049,513) magnitude -> tensordot(W, S, 1) with
+    power 1 (Q6: pcen=True skips the squaring) -> expand_dims(-1)."""
+    if weights is None:
+        weights = mel_f(SR, N_MELS, FMIN, FMAX, N_FFT, BREAK_FREQ)
+    s = np.asarray(spec, dtype=dtype)
+    if power == 2:
+        s = s ** 2
+    return np.matmul(weights.astype(dtype), s)[..., None]
+
+
+# --------------------------------------------------------------------------------------
+# a10-a12  PCEN                                                      tfpcen.py:8-110
+# --------------------------------------------------------------------------------------
+def ema(x, smooth=0.04, dtype=np.float64, axis=1):
+    """tfpcen.py:8-39: w = clip(smooth,0,1); M[t] = w*x[t] + (1-w)*M[t-1], M[-1] := x[:,0]
+    (tfpcen.py:92), scanned sequentially along `axis` (reference: axis 1 of [B,T,F])."""
+    x = np.moveaxis(np.asarray(x, dtype=dtype), axis, 0)
+    w = dtype(min(max(smooth, 0.0), 1.0))
+    one_m_w = dtype(1.0) - w
+    out = np.empty_like(x)
+    acc = x[0]
+    for t in range(x.shape[0]):
+        acc = w * x[t] + one_m_w * acc
+        out[t] = acc
+    return np.moveaxis(out, 0, axis)
+
+
+def normalize_minmax(x, dtype=np.float64):
+    """tfpcen.py:105-110 / tfdataset.py:1897-1902: 2*((x-min)/(max-min)) - 1 with min/max over
+    the whole tensor, batch included (Q14)."""
+    x = np.asarray(x, dtype=dtype)
+    mx, mn = np.max(x), np.min(x)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return dtype(2) * ((x - mn) / (mx - mn)) - dtype(1)
+
+
+def pcen_raw(x, gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, dtype=np.float64, axis=1):
+    """tfpcen.py:89-95 without the final min-max."""
+    x = np.asarray(x, dtype=dtype)
+    g = dtype(min(gain, 1.0))
+    r = dtype(max(root, 1.0))
+    m = ema(x, smooth, dtype, axis)
+    inv_r = dtype(1.0) / r
+    b = dtype(bias)
+    return (x / (dtype(eps) + m) ** g + b) ** inv_r - b ** inv_r
+
+
+def pcen(x, gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, dtype=np.float64, axis=1):
+    """tfpcen.py:89-99 (the unused `a-power` weight, Q12, plays no part)."""
+    return normalize_minmax(pcen_raw(x, gain, bias, root, smooth, eps, dtype, axis), dtype)
+
+
+# --------------------------------------------------------------------------------------
+# a13 / a14 and friends
+# --------------------------------------------------------------------------------------
+def power_to_db(mel, dtype=np.float64):
+    """tfdataset.py:1906-1913: 10log10(max(1e-10,x)) - 10log10(max(1e-10,max x)), floored at
+    (max of the result) - 80, tensor-global."""
+    mel = np.asarray(mel, dtype=dtype)
+    ref = np.max(mel)
+    amin = dtype(1e-10)
+    out = dtype(10.0) * np.log10(np.maximum(amin, mel))
+    out = out - dtype(10.0) * np.log10(np.maximum(amin, ref))
+    return np.maximum(out, np.max(out) - dtype(80))
+
+
+def librosa_power_to_db(s, amin=1e-10, top_db=80.0):
+    """librosa.power_to_db(S, ref=np.max) (predict_utils.py:216-217)."""
+    s = np.asarray(s)
+    ref = np.max(s)
+    out = 10.0 * np.log10(np.maximum(amin, s)) - 10.0 * np.log10(np.maximum(amin, ref))
+    return np.maximum(out, out.max() - top_db)
+
+
+def normalize_std(x, dtype=np.float64, epsilon=1e-7):
+    """tfdataset.py:1883-1893: (x-mean)/(std + keras epsilon 1e-7), tensor-global, population
+    std (tf.math.reduce_std)."""
+    x = np.asarray(x, dtype=dtype)
+    return (x - np.mean(x, dtype=np.float64).astype(dtype)) / (
+        np.std(x, dtype=np.float64).astype(dtype) + dtype(epsilon))
+
+
+def mag_transform(x, a=-1.0, dtype=np.float64):
+    """badwinner2.py:32-49: x ** sigmoid(a), a initialised to -1 (exponent 0.26894)."""
+    x = np.asarray(x, dtype=dtype)
+    e = dtype(1.0) / (dtype(1.0) + np.exp(-dtype(a)))
+    return x ** e
+
+
+# --------------------------------------------------------------------------------------
+# a8  load_samples window arithmetic                              predict_utils.py:9-150
+# --------------------------------------------------------------------------------------
+@dataclass
+class Track:
+    start: float
+    end: float
+    freq_start: float | None = None
+    freq_end: float | None = None
+
+    @property
+    def length(self):
+        return self.end - self.start
+
+
+def load_samples_windows(n_frames, sr, tracks, segment_length=3, stride=1, fmin=FMIN, fmax=FMAX,
+                         pad_short_tracks=False, rand_offset=None):
+    """Integer window arithmetic of predict_utils.load_samples (:53-147), no features.
+
+    Returns list[track] of list[(src_start, src_len, pad_left)]: window = `src_len` samples of the
+    recording starting at `src_start`, placed at `pad_left` inside a zero buffer of `sample_size`.
+    `rand_offset(extra)` stands in for np.random.randint(0, extra) (:118)."""
+    if rand_offset is None:
+        rand_offset = lambda extra: 0  # noqa: E731
+    sample_size = int(sr * segment_length)
+    out = []
+    for t in tracks:
+        wins = []
+        if (t.freq_start is not None and t.freq_end is not None
+                and (t.freq_start > fmax or t.freq_end < fmin)):  # :61-68
+            out.append(wins)
+            continue
+        start = 0
+        s_end = int(t.end * sr)
+        s_start = int(sr * t.start)
+        if not pad_short_tracks:  # :80-99 (the :75-77 branch keeps s_start/s_end as they are)
+            missing = sample_size - (s_end - s_start)
+            if missing > 0:
+                offset = missing // 2
+                s_start -= offset
+                if s_start <= 0:
+                    s_start = 0
+                    s_end = min(sample_size, n_frames)
+                else:
+                    end_offset = s_end + missing - offset
+                    if end_offset > n_frames:
+                        end_offset = n_frames
+                        s_start = max(end_offset - sample_size, 0)
+                    s_end = end_offset
+        # python slice frames[s_start:s_end] clamps to the array (:77, :99)
+        lo = min(max(s_start, 0), n_frames)
+        hi = min(max(s_end, lo), n_frames)
+        base, base_len = lo, hi - lo
+        w_start = 0
+        w_end = min(s_end, sample_size)  # :101-102 (Q11: absolute index vs length)
+        while True:  # :114-147
+            lo = min(w_start, base_len)
+            hi = min(max(w_end, lo), base_len)
+            n = hi - lo
+            pad_left = 0
+            if n != sample_size:
+                extra = sample_size - n
+                pad_left = rand_offset(extra)
+            wins.append((base + lo, n, pad_left))
+            start = start + stride
+            end = start + segment_length
+            w_start = int(start * sr)
+            w_end = min(int(end * sr), w_start + sample_size)
+            if end > t.length:
+                break
+        out.append(wins)
+    return out
+
+
+def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=HOP,
+                 mel_break=BREAK_FREQ, n_mels=N_MELS, fmin=FMIN, fmax=FMAX, channels=1, power=2,
+                 db_scale=False, normalize_clip=True, n_fft=N_FFT, pad_short_tracks=False,
+                 rand_offset=None, pad_mode="constant", dtype=np.float64):
+    """predict_utils.load_samples (:9-150), default branches, on top of the window table."""
+    frames = np.asarray(frames)
+    size = int(sr * segment_length)
+    result = []
+    for wins in load_samples_windows(len(frames), sr, tracks, segment_length, stride, fmin, fmax,
+                                     pad_short_tracks, rand_offset):
+        feats = []
+        for (s0, n, left) in wins:
+            data = np.zeros(size, dtype=frames.dtype)
+            data[left:left + n] = frames[s0:s0 + n]
+            if normalize_clip:
+                data = normalize(data, dtype=np.float32 if frames.dtype == np.float32 else np.float64)
+            feats.append(get_spect(data, sr, hop_length, mel_break, n_mels, fmin, fmax, n_fft, power,
+                                   db_scale, channels, pad_mode, dtype))
+        result.append(feats)
+    return result
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY 8(d) synthetic clip generator
+# --------------------------------------------------------------------------------------
+def synth_clips(indices, n=CLIP_SAMPLES, sr=SR, seed=20240):
+    """Clip i (global index -> sharding invariant) from a counter-based RNG keyed (seed, i):
+    0.3*U(-1,1) noise + 3 linear chirps (amp U(.05,.5), 300..11000 Hz start/end) + DC U(-.1,.1)."""
+    indices = np.atleast_1d(np.asarray(indices, dtype=np.int64))
+    out = np.empty((len(indices), n), dtype=np.float32)
+    t = np.arange(n, dtype=np.float64) / sr
+    dur = n / sr
+    for row, i in enumerate(indices):
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[int(i), 0, 0, 0]))
+        x = 0.3 * rng.uniform(-1.0, 1.0, n)
+        for _ in range(3):
+            a = rng.uniform(0.05, 0.5)
+            f0 = rng.uniform(300.0, 11000.0)
+            f1 = rng.uniform(300.0, 11000.0)
+            c = (f1 - f0) / dur
+            x += a * np.sin(2.0 * np.pi * (f0 * t + 0.5 * c * t * t))
+        x += rng.uniform(-0.1, 0.1)
+        out[row] = x.astype(np.float32)
+    return out
+
+
+def within_tolerance(ours, truth, rel=REL_TOL, abs_=ABS_TOL):
+    """North-star acceptance: |ours - truth| <= rel*|truth| + abs.  Returns (ok, worst_ratio)."""
+    ours = np.asarray(ours, dtype=np.float64)
+    truth = np.asarray(truth, dtype=np.float64)
+    budget = rel * np.abs(truth) + abs_
+    ratio = np.abs(ours - truth) / budget
+    worst = float(np.nanmax(ratio)) if ratio.size else 0.0
+    same_nan = np.array_equal(np.isnan(ours), np.isnan(truth))
+    return bool(worst <= 1.0 and same_nan), worst
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline ("port" of the reference's own op order, f32, all host threads)
+# --------------------------------------------------------------------------------------
+def reference_cpu_path(x, weights, workers=-1, with_pcen=True, channels=3):
+    """Config 1 of BASELINE.json, the way the reference executes it on CPU in f32:
+    normalize (tfdataset.py:1916) -> stft 4096/281 pad_end (:2026) -> z**2, transpose, abs (:2044-2046)
+    -> dense batch_dot with the weights replicated per clip (:2049-2051) -> repeat x3 (:2053)
+    -> PCEN on [B,T,F] (tfpcen.py:89-99).  scipy pocketfft with `workers` threads stands in for
+    TF's CPU FFT."""
+    x = normalize(x, np.float32)
+    frames = frame_tf(x, N_FFT, HOP, True) * hann_periodic(N_FFT, np.float32)
+    z = _sfft.rfft(frames, axis=-1, workers=workers)
+    p = np.abs(np.swapaxes(z ** 2, 1, 2))
+    w = np.repeat(weights[None], x.shape[0], axis=0)
+    img = np.matmul(w, p)
+    out = np.repeat(img[..., None], channels, axis=3) if channels else img
+    if with_pcen:
+        return out, pcen(np.swapaxes(img, 1, 2), dtype=np.float32)
+    return out, None

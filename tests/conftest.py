@@ -1,0 +1,39 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(GOLDEN, "frontend.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_banks():
+    return np.load(os.path.join(GOLDEN, "filterbanks.npz"))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import frontend_oracle
+    return frontend_oracle
+
+
+@pytest.fixture(scope="session")
+def clips(oracle, golden):
+    x = oracle.synth_clips(golden["clip_indices"])
+    assert float(np.sum(x, dtype=np.float64)) == float(golden["clips_checksum"][0]), \
+        "synthetic generator drifted from the one the golden vectors were made with"
+    return x

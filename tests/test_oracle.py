@@ -1,0 +1,204 @@
+"""CPU: the oracle against the golden vectors made by executing the reference's own source
+(oracle/ref_shim/gen_golden.py), plus closed-form known-answer tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+# ---------------------------------------------------------------- a4 filterbank
+def test_filterbank_bit_exact_vs_reference(oracle, golden_banks):
+    for tag in [k for k in golden_banks.files if not k.endswith("_args")]:
+        sr, n_mels, fmin, fmax, n_fft, brk = golden_banks[tag + "_args"]
+        w = oracle.mel_f(int(sr), int(n_mels), fmin, fmax, int(n_fft), brk)
+        assert w.dtype == np.float32
+        assert np.array_equal(w, golden_banks[tag]), tag
+
+
+@pytest.mark.parametrize("fmin,nnz,lo,hi", [(100, 1844, 9, 938), (500, 1777, 43, 938), (50, 1852, 5, 938)])
+def test_filterbank_kat(oracle, fmin, nnz, lo, hi):
+    w = oracle.mel_f(48000, 160, fmin, 11000, 4096, 1000)
+    assert w.shape == (160, 2049)
+    assert int(np.count_nonzero(w)) == nnz
+    cols = np.nonzero(w.any(axis=0))[0]
+    assert (cols.min(), cols.max()) == (lo, hi)
+    assert (w >= 0).all()
+    per_row = np.count_nonzero(w, axis=1)
+    assert per_row.min() >= 2 and per_row.max() <= 30
+    # every bin feeds at most two (adjacent) bands -- the banded kernels rely on it
+    assert np.count_nonzero(w, axis=0).max() <= 2
+
+
+def test_filterbank_empty_rows(oracle):
+    w = oracle.mel_f(48000, 160, 100, 3000, 1024, 1000)
+    assert int((w.max(axis=1) == 0).sum()) == 44
+
+
+# ---------------------------------------------------------------- a2 frame geometry
+@pytest.mark.parametrize("fl,step,pad,T", [(4096, 281, True, 513), (4096, 281, False, 498), (2048, 278, False, 511),
+                                           (1024, 280, False, 511), (1024, 281, True, 513), (4800, 281, True, 513)])
+def test_frame_counts(oracle, fl, step, pad, T):
+    assert oracle.num_frames_tf(144000, fl, step, pad) == T
+    x = np.arange(144000, dtype=np.float32)
+    fr = oracle.frame_tf(x, fl, step, pad)
+    assert fr.shape == (T, fl)
+    assert fr[1, 0] == step
+    if pad and fl == 4096:
+        first_partial = next(t for t in range(T) if step * t + fl > 144000)
+        assert first_partial == 498
+        assert fl + step * (T - 1) - 144000 == 3968
+        assert np.count_nonzero(fr[512]) == 128
+
+
+def test_center_frame_count(oracle):
+    assert oracle.num_frames_center(144000, 281) == 513
+    fr = oracle.frame_center(np.arange(1, 144001, dtype=np.float32), 4096, 281)
+    assert fr.shape == (513, 4096)
+    assert fr[0, 2047] == 0 and fr[0, 2048] == 1
+
+
+# ---------------------------------------------------------------- golden: normalize / paths / PCEN
+def test_normalize_bit_exact(oracle, golden):
+    got = oracle.normalize(golden["small"], np.float32)
+    assert np.array_equal(got, golden["norm_np"])
+    assert np.array_equal(got, golden["norm_tf"])
+    assert np.isnan(oracle.normalize(np.full((1, 16), 0.25, np.float32))).all()
+    assert np.isnan(golden["const_clip"]).all()
+
+
+def test_clips_normalize(oracle, golden, clips):
+    assert np.array_equal(oracle.normalize(clips, np.float32)[:, :64], golden["clips_norm_head"])
+
+
+def _check(oracle, got, want, scale=1.0):
+    ok, worst = oracle.within_tolerance(got, want, oracle.REL_TOL * scale, oracle.ABS_TOL * scale)
+    assert ok, f"worst error = {worst:.3f} x budget"
+    return worst
+
+
+def test_path_a_f32_and_f64(oracle, golden, clips):
+    xn = oracle.normalize(clips, np.float32)
+    w = oracle.mel_f(48000, 160, 100, 11000, 4096, 1000)
+    f32 = oracle.raw_to_mel(xn, w, channels=0, dtype=np.float32)
+    assert f32.shape == (2, 160, 513)
+    _check(oracle, f32, golden["path_a"], 0.05)      # same op order: rounding noise only
+    f64 = oracle.raw_to_mel(xn, w, channels=0, dtype=np.float64)
+    _check(oracle, golden["path_a"], f64)            # the reference's f32 result sits inside the budget
+    assert oracle.raw_to_mel(xn[0], w, channels=3, dtype=np.float32).shape == (160, 513, 3)
+
+
+def test_path_b(oracle, golden, clips):
+    xn = oracle.normalize(clips, np.float32)
+    for i in range(2):
+        got = oracle.get_spect(xn[i], dtype=np.float32)
+        assert got.shape == (160, 513, 1)
+        _check(oracle, got[..., 0], golden["path_b"][i], 0.05)
+        _check(oracle, golden["path_b"][i], oracle.get_spect(xn[i], dtype=np.float64)[..., 0])
+
+
+def test_path_c(oracle, golden, clips):
+    xn = oracle.normalize(clips[:1], np.float32)
+    mag = np.abs(oracle.stft_librosa(xn[0], dtype=np.float32))
+    assert mag.shape == (2049, 513)
+    got = oracle.mel_from_spectrogram(mag, dtype=np.float32)
+    _check(oracle, got[..., 0], golden["path_c"], 0.05)
+
+
+def test_pcen_golden(oracle, golden):
+    x = np.swapaxes(golden["path_a"], 1, 2)
+    assert np.array_equal(oracle.ema(x, dtype=np.float32), golden["ema"])
+    _check(oracle, oracle.pcen(x, dtype=np.float32), golden["pcen"], 0.05)
+    _check(oracle, golden["pcen"], oracle.pcen(x, dtype=np.float64))
+    s = golden["small_btf"]
+    _check(oracle, oracle.pcen(s, dtype=np.float32), golden["pcen_small"], 0.05)
+    _check(oracle, oracle.pcen(s, gain=1.3, root=0.5, bias=1.5, smooth=0.25, dtype=np.float32),
+           golden["pcen_small2"], 0.05)
+    assert np.array_equal(oracle.normalize_minmax(s, np.float32), golden["minmax_small"])
+    assert list(golden["pcen_weight_names"]) == ["gain", "bias", "root", "a-power", "EMA/smooth"]
+    assert np.allclose(golden["pcen_weight_values"], [0.98, 2.0, 2.0, -1.0, 0.04])
+    # Q12: both layers register under one serialisation key in the reference
+    assert list(golden["pcen_serial_key"]) == ["MyLayers>MagTransform", "MyLayers>MagTransform"]
+
+
+def test_compress_golden(oracle, golden):
+    mel = golden["path_a"][0]
+    _check(oracle, oracle.power_to_db(mel, np.float32), golden["power_to_db"], 0.5)  # 1-ulp log10 scalar-vs-array differences shift every dB value
+    _check(oracle, oracle.normalize_std(mel, np.float32), golden["normalize_std"], 0.05)
+    assert np.array_equal(oracle.normalize_minmax(mel, np.float32), golden["normalize_minmax"])
+    _check(oracle, oracle.mag_transform(mel, dtype=np.float32), golden["mag_transform"], 0.05)
+    lim = golden["normalize_minmax"]
+    assert lim.min() == -1.0 and lim.max() == 1.0           # tfdataset.py:1442-1472 invariant
+
+
+# ---------------------------------------------------------------- a8 load_samples windows (integer: bit-exact)
+def test_load_samples_windows(oracle):
+    with open(os.path.join(GOLDEN, "load_samples.json")) as fh:
+        cases = json.load(fh)
+    assert len(cases) >= 4
+    for case in cases:
+        offs = [v for (_, v) in case["offsets"]]
+        his = [h for (h, _) in case["offsets"]]
+        seen_his = []
+
+        def rand_offset(extra, _o=offs, _h=seen_his):
+            _h.append(extra)
+            return _o[len(_h) - 1]
+
+        tracks = [oracle.Track(*t) for t in case["tracks"]]
+        wins = oracle.load_samples_windows(int(case["total"] * 48000), 48000, tracks, rand_offset=rand_offset)
+        assert [len(w) for w in wins] == case["counts"]
+        flat = [list(w) for tw in wins for w in tw]
+        want = [list(w) for w in case["windows"]]
+        assert flat == want
+        assert seen_his == his
+
+
+# ---------------------------------------------------------------- analytic KATs
+def test_impulse_indexing(oracle):
+    s = 100000
+    x = np.zeros(144000)
+    x[s] = 1.0
+    z = oracle.stft_tf(x, dtype=np.float64)
+    p = z.real ** 2 + z.imag ** 2
+    w = oracle.hann_periodic(4096)
+    for t in range(513):
+        n = s - 281 * t
+        want = w[n] ** 2 if 0 <= n < 4096 else 0.0
+        assert np.allclose(p[t], want, atol=1e-12)
+
+
+def test_sine_bin_centre(oracle):
+    k0 = 300
+    n = np.arange(144000)
+    x = np.sin(2 * np.pi * k0 * n / 4096.0)
+    z = np.abs(oracle.stft_tf(x, dtype=np.float64))
+    assert np.allclose(z[10, k0], 4096 * 0.25, rtol=1e-9)
+    assert np.allclose(z[10, k0 - 1], 4096 * 0.125, rtol=1e-9)
+    assert np.allclose(z[10, k0 + 1], 4096 * 0.125, rtol=1e-9)
+    assert z[10, k0 + 5] < 1e-7
+
+
+def test_ema_closed_forms(oracle):
+    const = np.full((1, 50, 3), 2.5)
+    assert np.allclose(oracle.ema(const), 2.5)
+    imp = np.zeros((1, 50, 1))
+    imp[0, 5, 0] = 1.0
+    m = oracle.ema(imp, smooth=0.04)[0, :, 0]
+    t = np.arange(50)
+    want = np.where(t >= 5, 0.04 * 0.96 ** np.maximum(t - 5, 0), 0.0)
+    assert np.allclose(m, want, atol=1e-15)
+    x = np.full((1, 20, 2), 3.0)
+    raw = oracle.pcen_raw(x)
+    assert np.allclose(raw, (3.0 / (1e-6 + 3.0) ** 0.98 + 2.0) ** 0.5 - 2.0 ** 0.5)
+    two = np.array([1.0, 5.0, 1.0, 5.0])
+    assert np.array_equal(oracle.normalize_minmax(two), [-1, 1, -1, 1])
+
+
+def test_generator_is_index_keyed(oracle):
+    a = oracle.synth_clips([5, 9], n=4096)
+    b = oracle.synth_clips([9], n=4096)
+    assert np.array_equal(a[1], b[0])
+    assert a.dtype == np.float32 and np.abs(a).max() < 2.0
