@@ -1,0 +1,139 @@
+"""ctypes binding of libcacfe.so (C ABI in include/cacfe.h).
+
+The shared library is built in-tree by `build()` (nvcc, sm_100a only).  There is no fallback of any kind: if
+the library is missing, or a call fails, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libcacfe.so")
+SOURCES = ["cacfe.cu"]
+HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_pcen.cuh",
+           "k_compress.cuh", "k_melspec.cuh", os.path.join("..", "..", "include", "cacfe.h")]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# enums (include/cacfe.h)
+OK = 0
+FRAME_TF_PAD_END, FRAME_CENTER_ZERO, FRAME_CENTER_REFLECT, FRAME_NO_PAD = 0, 1, 2, 3
+LAYOUT_BMTC, LAYOUT_BTM = 0, 1
+MEL_BANDED_FP32, MEL_TC_3XTF32 = 0, 1
+NORM_TENSOR, NORM_CLIP, NORM_NONE = 0, 1, 2
+COMPRESS_MAG_POW, COMPRESS_POWER_TO_DB, COMPRESS_MINMAX, COMPRESS_STD = 0, 1, 2, 3
+STATUS_NAMES = {0: "CACFE_OK", -1: "CACFE_EINVAL", -2: "CACFE_ESHAPE", -3: "CACFE_EDTYPE", -4: "CACFE_EDEVICE",
+                -5: "CACFE_EALIGN", -6: "CACFE_ECUDA", -7: "CACFE_ENOMEM"}
+
+
+class Config(Structure):
+    _fields_ = [("sr", c_int32), ("n_samples", c_int32), ("n_fft", c_int32), ("hop", c_int32), ("framing", c_int32),
+                ("n_mels", c_int32), ("fmin", c_double), ("fmax", c_double), ("break_freq", c_double),
+                ("power", c_int32), ("channels", c_int32), ("out_layout", c_int32), ("mel_impl", c_int32),
+                ("normalize", c_int32), ("reserved", c_int32), ("filterbank", POINTER(c_float))]
+
+
+class PcenParams(Structure):
+    _fields_ = [("gain", c_float), ("bias", c_float), ("root", c_float), ("smooth", c_float), ("eps", c_float),
+                ("norm_scope", c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/cacfe.h declares
+PROTOTYPES = {
+    "cacfe_version": (c_int, []),
+    "cacfe_last_error": (c_char_p, []),
+    "cacfe_mel_filterbank": (c_int, [c_int, c_int, c_double, c_double, c_int, c_double, POINTER(c_float)]),
+    "cacfe_num_frames": (c_int, [c_int, c_int, c_int, c_int]),
+    "cacfe_plan_create": (c_int, [POINTER(Config), c_int, POINTER(c_void_p)]),
+    "cacfe_plan_destroy": (None, [c_void_p]),
+    "cacfe_plan_num_frames": (c_int, [c_void_p]),
+    "cacfe_plan_num_bins": (c_int, [c_void_p]),
+    "cacfe_plan_filterbank": (c_int, [c_void_p, POINTER(c_float)]),
+    "cacfe_plan_bin_range": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "cacfe_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "cacfe_pcen_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int]),
+    "cacfe_compress_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
+    "cacfe_plan_launch_count": (c_longlong, [c_void_p]),
+    "cacfe_plan_profile": (c_int, [c_void_p, c_int]),
+    "cacfe_plan_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
+    "cacfe_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]),
+    "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cacfe_mel_from_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cacfe_ema": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "cacfe_pcen": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int, c_longlong, c_int, c_int,
+                           c_void_p, c_void_p]),
+    "cacfe_compress": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p,
+                               c_void_p]),
+    "cacfe_frontend_pcen": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cacfe_hostpipe_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "cacfe_hostpipe_destroy": (None, [c_void_p]),
+    "cacfe_hostpipe_run": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int]),
+    "cacfe_hostpipe_device_bytes": (c_size_t, [c_void_p]),
+    "cacfe_host_register": (c_int, [c_void_p, c_size_t]),
+    "cacfe_host_unregister": (c_int, [c_void_p]),
+    "cacfe_frontend_dlpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cacfe_pcen_dlpack": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class CacfeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> audio-training_b200/libcacfe.so"""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load libcacfe.so.  Raises ImportError (loudly) when it has not been built: there is no other path."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  audio-training_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def check(code):
+    if code != OK:
+        raise CacfeError(code, load().cacfe_last_error().decode("utf-8", "replace"))
+    return code

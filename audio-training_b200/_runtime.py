@@ -1,0 +1,321 @@
+"""Plans, workspaces and tensor plumbing between the reference-named Python API and the C ABI.
+
+PyTorch is used for device memory, streams and host<->device copies only; every arithmetic step of the hot
+path runs in libcacfe.so.  Nothing here computes features on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass, replace
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CacfeError, Config, PcenParams  # noqa: F401
+
+_FRAMING = {"tf_pad_end": _lib.FRAME_TF_PAD_END, "center_zero": _lib.FRAME_CENTER_ZERO,
+            "center_reflect": _lib.FRAME_CENTER_REFLECT, "no_pad": _lib.FRAME_NO_PAD}
+_LAYOUT = {"bmtc": _lib.LAYOUT_BMTC, "btm": _lib.LAYOUT_BTM}
+_SCOPE = {"tensor": _lib.NORM_TENSOR, "clip": _lib.NORM_CLIP, "none": _lib.NORM_NONE}
+_COMPRESS = {"mag_pow": _lib.COMPRESS_MAG_POW, "power_to_db": _lib.COMPRESS_POWER_TO_DB,
+             "minmax": _lib.COMPRESS_MINMAX, "std": _lib.COMPRESS_STD}
+
+
+@dataclass(frozen=True)
+class FrontendConfig:
+    """One immutable description of the feature path (replaces the reference's mutable module globals
+    FMIN/FMAX/NFFT/N_MELS/BREAK_FREQ/MEL_WEIGHTS, tfdataset.py:42-57,429-460)."""
+    sr: int = 48000
+    n_samples: int = 144000
+    n_fft: int = 4096
+    hop: int = 281
+    framing: str = "tf_pad_end"
+    n_mels: int = 160
+    fmin: float = 100.0
+    fmax: float = 11000.0
+    break_freq: float = 1000.0
+    power: int = 2
+    channels: int = 3
+    out_layout: str = "bmtc"
+    normalize: bool = False
+
+    def with_(self, **kw):
+        return replace(self, **kw)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def pcen_params(gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, norm_scope="tensor"):
+    return PcenParams(float(gain), float(bias), float(root), float(smooth), float(eps), _SCOPE[norm_scope])
+
+
+class Plan:
+    """A cacfe_plan plus its (growing) device workspace.  One per (config, device, filterbank)."""
+
+    def __init__(self, config: FrontendConfig, device: int = 0, filterbank: np.ndarray | None = None):
+        lib = _lib.load()
+        self.config = config
+        self.device = int(device)
+        self._lib = lib
+        self._handle = ctypes.c_void_p(0)
+        self._ws = None
+        self._ws_lock = threading.Lock()
+        cfg = Config()
+        cfg.sr, cfg.n_samples, cfg.n_fft, cfg.hop = config.sr, config.n_samples, config.n_fft, config.hop
+        cfg.framing = _FRAMING[config.framing]
+        cfg.n_mels, cfg.fmin, cfg.fmax, cfg.break_freq = config.n_mels, config.fmin, config.fmax, config.break_freq
+        cfg.power, cfg.channels = config.power, config.channels
+        cfg.out_layout = _LAYOUT[config.out_layout]
+        cfg.mel_impl = _lib.MEL_BANDED_FP32
+        cfg.normalize = 1 if config.normalize else 0
+        self._bank_keepalive = None
+        if filterbank is not None:
+            fb = np.ascontiguousarray(filterbank, dtype=np.float32)
+            if fb.shape != (config.n_mels, 1 + config.n_fft // 2):
+                raise ValueError(f"filterbank shape {fb.shape} != {(config.n_mels, 1 + config.n_fft // 2)}")
+            self._bank_keepalive = fb
+            cfg.filterbank = fb.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        _lib.check(lib.cacfe_plan_create(ctypes.byref(cfg), self.device, ctypes.byref(self._handle)))
+        self.n_frames = lib.cacfe_plan_num_frames(self._handle)
+        self.n_bins = lib.cacfe_plan_num_bins(self._handle)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                self._lib.cacfe_plan_destroy(self._handle)
+                self._handle = ctypes.c_void_p(0)
+        except Exception:
+            pass
+
+    # ---- introspection -------------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._handle
+
+    def filterbank(self):
+        out = np.empty((self.config.n_mels, self.n_bins), dtype=np.float32)
+        _lib.check(self._lib.cacfe_plan_filterbank(self._handle, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        return out
+
+    def bin_range(self):
+        lo, hi = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self._lib.cacfe_plan_bin_range(self._handle, ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def launch_count(self):
+        return int(self._lib.cacfe_plan_launch_count(self._handle))
+
+    def profile(self, enable=True):
+        _lib.check(self._lib.cacfe_plan_profile(self._handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> (summed ms of the fused STFT/mel kernel launches since the last read, number of launches)"""
+        ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+        _lib.check(self._lib.cacfe_plan_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def feature_shape(self, B):
+        c = self.config
+        if c.out_layout == "btm":
+            return (B, self.n_frames, c.n_mels)
+        return (B, c.n_mels, self.n_frames, c.channels)
+
+    # ---- workspace ----------------------------------------------------------------------------------
+    def workspace(self, nbytes):
+        with self._ws_lock:
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=f"cuda:{self.device}")
+            return self._ws
+
+    def workspace_for(self, B):
+        return self.workspace(self._lib.cacfe_workspace_bytes(self._handle, int(B)))
+
+    # ---- operators (device tensors in, device tensors out) ------------------------------------------
+    def _check_in(self, x, what):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise TypeError(f"{what}: CUDA tensor required")
+        if x.device.index != self.device:
+            raise ValueError(f"{what}: tensor on {x.device}, plan on cuda:{self.device}")
+        if x.dtype != torch.float32:
+            raise TypeError(f"{what}: float32 required, got {x.dtype}")
+        return x if x.is_contiguous() else x.contiguous()
+
+    def normalize(self, x):
+        x = self._check_in(x, "normalize")
+        n = x.shape[-1]
+        rows = x.numel() // n
+        out = torch.empty_like(x)
+        ws = self.workspace_for(rows)
+        _lib.check(self._lib.cacfe_normalize(self._handle, _ptr(x), _ptr(out), rows, n, _ptr(ws), _stream(self.device)))
+        return out
+
+    def frontend(self, raw, out=None):
+        raw = self._check_in(raw, "frontend")
+        if raw.dim() != 2 or raw.shape[1] != self.config.n_samples:
+            raise ValueError(f"frontend: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
+        B = raw.shape[0]
+        if out is None:
+            out = torch.empty(self.feature_shape(B), dtype=torch.float32, device=raw.device)
+        ws = self.workspace_for(B)
+        _lib.check(self._lib.cacfe_frontend(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
+        return out
+
+    def frontend_pcen(self, raw, params=None, out=None):
+        raw = self._check_in(raw, "frontend_pcen")
+        B = raw.shape[0]
+        if out is None:
+            out = torch.empty((B, self.n_frames, self.config.n_mels), dtype=torch.float32, device=raw.device)
+        ws = self.workspace_for(B)
+        params = params or pcen_params()
+        _lib.check(self._lib.cacfe_frontend_pcen(self._handle, ctypes.byref(params), _ptr(raw), _ptr(out), B, _ptr(ws),
+                                                 _stream(self.device)))
+        return out
+
+    def mel_from_spectrogram(self, spec):
+        spec = self._check_in(spec, "mel_from_spectrogram")
+        if spec.dim() != 3 or spec.shape[1] != self.n_bins:
+            raise ValueError(f"mel_from_spectrogram: expected [B, {self.n_bins}, T], got {tuple(spec.shape)}")
+        B, _, T = spec.shape
+        c = self.config
+        shape = (B, T, c.n_mels) if c.out_layout == "btm" else (B, c.n_mels, T, c.channels)
+        out = torch.empty(shape, dtype=torch.float32, device=spec.device)
+        _lib.check(self._lib.cacfe_mel_from_spectrogram(self._handle, _ptr(spec), _ptr(out), B, T, _stream(self.device)))
+        return out
+
+    def ema(self, x, smooth, time_axis=1):
+        x = self._check_in(x, "ema")
+        B, opc, T, inner = _split_axes(x, time_axis)
+        out = torch.empty_like(x)
+        _lib.check(self._lib.cacfe_ema(self._handle, float(smooth), _ptr(x), _ptr(out), B, opc, T, inner,
+                                       _stream(self.device)))
+        return out
+
+    def pcen(self, x, params=None, time_axis=1):
+        x = self._check_in(x, "pcen")
+        B, opc, T, inner = _split_axes(x, time_axis)
+        out = torch.empty_like(x)
+        params = params or pcen_params()
+        ws = self.workspace(self._lib.cacfe_pcen_workspace_bytes(B, opc, inner))
+        _lib.check(self._lib.cacfe_pcen(self._handle, ctypes.byref(params), _ptr(x), _ptr(out), B, opc, T, inner,
+                                        _ptr(ws), _stream(self.device)))
+        return out
+
+    def compress(self, x, mode, param=0.0, per_clip=False):
+        x = self._check_in(x, "compress")
+        entries = x.shape[0] if per_clip else 1
+        per_entry = x.numel() // entries
+        out = torch.empty_like(x)
+        ws = self.workspace(self._lib.cacfe_compress_workspace_bytes(entries, per_entry))
+        _lib.check(self._lib.cacfe_compress(self._handle, _COMPRESS[mode], float(param), _ptr(x), _ptr(out), entries,
+                                            per_entry, _ptr(ws), _stream(self.device)))
+        return out
+
+
+def _split_axes(x, time_axis):
+    """View x as [B][outer_per_clip][T][inner] around `time_axis` (axis 0 is the batch)."""
+    if x.dim() < 2:
+        raise ValueError("expected at least [batch, time]")
+    time_axis = time_axis % x.dim()
+    if time_axis == 0:
+        raise ValueError("axis 0 is the batch axis")
+    B = x.shape[0]
+    opc = 1
+    for d in x.shape[1:time_axis]:
+        opc *= d
+    inner = 1
+    for d in x.shape[time_axis + 1:]:
+        inner *= d
+    return B, opc, x.shape[time_axis], inner
+
+
+class HostPipe:
+    """cacfe_hostpipe: host buffers in, host buffers out (chunked H2D / kernels / D2H on two streams)."""
+
+    def __init__(self, plan: Plan, max_B: int, chunk: int = 256):
+        self.plan = plan
+        self.max_B = int(max_B)
+        self._lib = plan._lib
+        self._handle = ctypes.c_void_p(0)
+        _lib.check(self._lib.cacfe_hostpipe_create(plan.handle, self.max_B, int(chunk), ctypes.byref(self._handle)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                self._lib.cacfe_hostpipe_destroy(self._handle)
+                self._handle = ctypes.c_void_p(0)
+        except Exception:
+            pass
+
+    def device_bytes(self):
+        return int(self._lib.cacfe_hostpipe_device_bytes(self._handle))
+
+    def run(self, host_in, host_out=None, params=None):
+        """host_in: float32 [B, n_samples] numpy array or CPU tensor (pinned for full PCIe rate).
+        params=None -> mel image in the plan's layout; PcenParams -> PCEN output [B, T, n_mels]."""
+        is_np = isinstance(host_in, np.ndarray)
+        tin = torch.from_numpy(host_in) if is_np else host_in
+        if tin.is_cuda or tin.dtype != torch.float32 or not tin.is_contiguous():
+            raise TypeError("HostPipe.run: contiguous float32 host buffer required")
+        B = tin.shape[0]
+        c = self.plan.config
+        shape = (B, self.plan.n_frames, c.n_mels) if params is not None else self.plan.feature_shape(B)
+        if host_out is None:
+            tout = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        else:
+            tout = torch.from_numpy(host_out) if isinstance(host_out, np.ndarray) else host_out
+            if tuple(tout.shape) != tuple(shape) or tout.dtype != torch.float32 or not tout.is_contiguous():
+                raise ValueError(f"HostPipe.run: host_out must be contiguous float32 {shape}")
+        _lib.check(self._lib.cacfe_hostpipe_run(self._handle, ctypes.byref(params) if params is not None else None,
+                                                ctypes.c_void_p(tin.data_ptr()), ctypes.c_void_p(tout.data_ptr()), B))
+        if host_out is not None:
+            return host_out
+        return tout.numpy() if is_np else tout
+
+
+# ---- plan cache ------------------------------------------------------------------------------------------
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise CacfeError(-6, "no CUDA device: audio-training_b200 has no CPU path")
+    return torch.cuda.current_device()
+
+
+def get_plan(config: FrontendConfig, device: int | None = None, filterbank: np.ndarray | None = None) -> Plan:
+    device = default_device() if device is None else int(device)
+    key = (config, device, None if filterbank is None else hash(np.ascontiguousarray(filterbank, np.float32).tobytes()))
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is None:
+            plan = Plan(config, device, filterbank)
+            _plans[key] = plan
+        return plan
+
+
+def clear_plans():
+    with _plans_lock:
+        _plans.clear()
+
+
+# ---- moving caller data on and off the device -----------------------------------------------------------------
+def to_device(x, device=None):
+    """-> (float32 CUDA tensor, restore) where restore(t) gives the result back in the caller's flavour
+    (numpy in -> numpy out, CPU tensor -> CPU tensor, CUDA tensor -> CUDA tensor)."""
+    device = default_device() if device is None else device
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x.to(torch.float32), (lambda t: t)
+        return x.to(device=f"cuda:{device}", dtype=torch.float32, non_blocking=True), (lambda t: t.cpu())
+    arr = np.asarray(x)
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(f"cuda:{device}", non_blocking=True)
+    return t, (lambda t: t.cpu().numpy())

@@ -1,0 +1,853 @@
+// cacfe C ABI (include/cacfe.h) over the sm_100a kernels in this directory.
+// Host side: plan (tables, filterbank in band form), argument checks, launches.  No CPU compute path.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cacfe.h"
+#include "k_compress.cuh"
+#include "k_frontend.cuh"
+#include "k_melspec.cuh"
+#include "k_pcen.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) return fail(CACFE_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+
+inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+constexpr int kMaxSplits = 16;
+
+}  // namespace
+
+struct cacfe_plan {
+  cacfe_config cfg;
+  int device = 0, sm_count = 0;
+  int n_frames = 0, n_bins = 0, bin_lo = 0, bin_hi = -1, nnz = 0, origin = 0, nq = 0;
+  std::vector<float> bank;  // host [n_mels][n_bins]
+  float2* d_tw = nullptr;
+  float* d_win = nullptr;
+  float* d_band_w = nullptr;
+  int* d_band_start = nullptr;
+  int* d_band_ofs = nullptr;
+  cacfe::K1Smem k1;
+  bool frontend_ok = false;
+  std::atomic<long long> launches{0};
+  // optional CUDA-event bracket around every K1 launch (bench.py's live per-kernel timing)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k1_events;
+};
+
+extern "C" {
+
+int cacfe_version(void) { return CACFE_VERSION; }
+const char* cacfe_last_error(void) { return g_err.c_str(); }
+
+// custommel.py:6-54 restated in double precision with numpy's evaluation order:
+//   linspace: start + i*step, last point pinned to `stop`;  rfftfreq: k * (1 / (n_fft * (1/sr))).
+int cacfe_mel_filterbank(int sr, int n_mels, double fmin, double fmax, int n_fft, double break_freq, float* out) {
+  if (sr <= 0 || n_mels <= 0 || n_fft <= 0 || break_freq <= 0 || out == nullptr)
+    return fail(CACFE_EINVAL, "mel_filterbank: bad arguments");
+  const int n_bins = 1 + n_fft / 2;
+  const int n_pts = n_mels + 2;
+  auto hz_to_mel = [&](double f) { return 2595.0 * std::log10(1.0 + f / break_freq); };
+  const double lo = hz_to_mel(fmin), hi = hz_to_mel(fmax);
+  std::vector<double> edge(n_pts);
+  const double step = (hi - lo) / (double)(n_pts - 1);
+  for (int i = 0; i < n_pts; ++i) {
+    const double mel = (i == n_pts - 1) ? hi : (double)i * step + lo;
+    edge[i] = break_freq * (std::pow(10.0, mel / 2595.0) - 1.0);
+  }
+  const double val = 1.0 / ((double)n_fft * (1.0 / (double)sr));
+  for (int m = 0; m < n_mels; ++m) {
+    const double d0 = edge[m + 1] - edge[m], d1 = edge[m + 2] - edge[m + 1];
+    const double enorm = 2.0 / (edge[m + 2] - edge[m]);
+    for (int k = 0; k < n_bins; ++k) {
+      const double f = (double)k * val;
+      const double lower = -(edge[m] - f) / d0;
+      const double upper = (edge[m + 2] - f) / d1;
+      const float w = (float)std::fmax(0.0, std::fmin(lower, upper));  // stored into the f32 array (custommel.py:37)
+      out[(size_t)m * n_bins + k] = (float)((double)w * enorm);         // f32 row *= f64 enorm (custommel.py:42)
+    }
+  }
+  return CACFE_OK;
+}
+
+int cacfe_num_frames(int n_samples, int n_fft, int hop, int framing) {
+  if (hop <= 0 || n_fft <= 0 || n_samples < 0) return fail(CACFE_EINVAL, "num_frames: bad arguments");
+  switch (framing) {
+    case CACFE_FRAME_TF_PAD_END: return (n_samples + hop - 1) / hop;
+    case CACFE_FRAME_CENTER_ZERO:
+    case CACFE_FRAME_CENTER_REFLECT: return 1 + n_samples / hop;
+    case CACFE_FRAME_NO_PAD: return n_samples < n_fft ? 0 : 1 + (n_samples - n_fft) / hop;
+    default: return fail(CACFE_EINVAL, "num_frames: unknown framing %d", framing);
+  }
+}
+
+int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
+  if (cfg == nullptr || out == nullptr) return fail(CACFE_EINVAL, "plan_create: null argument");
+  *out = nullptr;
+  if (cfg->n_fft < 8 || cfg->n_fft > (1 << 20) || (cfg->n_fft & 1))
+    return fail(CACFE_EINVAL, "plan_create: n_fft=%d out of range", cfg->n_fft);
+  if (cfg->hop < 1 || cfg->hop > 2048) return fail(CACFE_EINVAL, "plan_create: hop=%d out of range [1, 2048]", cfg->hop);
+  if (cfg->n_samples < 1) return fail(CACFE_EINVAL, "plan_create: n_samples must be positive");
+  if (cfg->power != 1 && cfg->power != 2) return fail(CACFE_EINVAL, "plan_create: power must be 1 or 2");
+  if (cfg->n_mels < 1 || cfg->n_mels > 1024) return fail(CACFE_EINVAL, "plan_create: n_mels out of range");
+  if (cfg->channels < 1 || cfg->channels > 16) return fail(CACFE_EINVAL, "plan_create: channels out of range");
+  if (cfg->out_layout != CACFE_LAYOUT_BMTC && cfg->out_layout != CACFE_LAYOUT_BTM)
+    return fail(CACFE_EINVAL, "plan_create: unknown out_layout");
+  if (cfg->out_layout == CACFE_LAYOUT_BTM && cfg->channels != 1)
+    return fail(CACFE_EINVAL, "plan_create: layout BTM has no channel axis (channels must be 1)");
+  if (cfg->framing < 0 || cfg->framing > 3) return fail(CACFE_EINVAL, "plan_create: unknown framing");
+  if (cfg->framing == CACFE_FRAME_CENTER_REFLECT && cfg->n_samples <= cfg->n_fft / 2)
+    return fail(CACFE_EINVAL, "plan_create: reflect padding needs n_samples > n_fft/2");
+  if (cfg->mel_impl != CACFE_MEL_BANDED_FP32)
+    return fail(CACFE_EINVAL, "plan_create: mel_impl %d not available in this build", cfg->mel_impl);
+
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(CACFE_ECUDA, "plan_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= count) return fail(CACFE_EDEVICE, "plan_create: device %d of %d", device, count);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(CACFE_EDEVICE, "plan_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+
+  cacfe_plan* p = new cacfe_plan();
+  p->cfg = *cfg;
+  p->cfg.filterbank = nullptr;
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->n_bins = 1 + cfg->n_fft / 2;
+  p->n_frames = cacfe_num_frames(cfg->n_samples, cfg->n_fft, cfg->hop, cfg->framing);
+  p->origin = (cfg->framing == CACFE_FRAME_CENTER_ZERO || cfg->framing == CACFE_FRAME_CENTER_REFLECT) ? -cfg->n_fft / 2 : 0;
+  if (p->n_frames < 1) {
+    delete p;
+    return fail(CACFE_ESHAPE, "plan_create: clip too short for one frame");
+  }
+  p->bank.resize((size_t)cfg->n_mels * p->n_bins);
+  if (cfg->filterbank != nullptr) {
+    std::memcpy(p->bank.data(), cfg->filterbank, p->bank.size() * sizeof(float));
+  } else {
+    int rc = cacfe_mel_filterbank(cfg->sr, cfg->n_mels, cfg->fmin, cfg->fmax, cfg->n_fft, cfg->break_freq, p->bank.data());
+    if (rc != CACFE_OK) {
+      delete p;
+      return rc;
+    }
+  }
+  // band form: per mel the run [first non-zero, last non-zero]
+  std::vector<float> bw;
+  std::vector<int> bfirst(cfg->n_mels, 0), bofs(cfg->n_mels + 1, 0);
+  int lo = p->n_bins, hi = -1;
+  for (int m = 0; m < cfg->n_mels; ++m) {
+    const float* row = p->bank.data() + (size_t)m * p->n_bins;
+    int a = -1, b = -1;
+    for (int k = 0; k < p->n_bins; ++k)
+      if (row[k] != 0.0f) {
+        if (a < 0) a = k;
+        b = k;
+      }
+    bofs[m] = (int)bw.size();
+    if (a >= 0) {
+      bfirst[m] = a;
+      for (int k = a; k <= b; ++k) bw.push_back(row[k]);
+      lo = a < lo ? a : lo;
+      hi = b > hi ? b : hi;
+    }
+  }
+  bofs[cfg->n_mels] = (int)bw.size();
+  if (hi < 0) {  // an all-zero bank is legal (every feature is 0): keep one dummy bin
+    lo = hi = 0;
+  }
+  for (int m = 0; m < cfg->n_mels; ++m) bfirst[m] = (bofs[m + 1] > bofs[m]) ? bfirst[m] - lo : 0;
+  p->bin_lo = lo;
+  p->bin_hi = hi;
+  p->nnz = (int)bw.size();
+  p->nq = hi / 64 + 1;
+  if (bw.empty()) bw.push_back(0.0f);
+
+  // The fused raw->mel kernel exists for n_fft = 4096 (the reference's only shipped configuration); other sizes
+  // get a plan for the spectrogram / PCEN / compression entry points and cacfe_frontend refuses them.
+  p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz);
+  p->frontend_ok = cfg->n_fft == cacfe::kFft && p->k1.total <= (size_t)prop.sharedMemPerBlockOptin;
+
+  // tables
+  std::vector<float2> tw(4096);
+  for (int k1 = 0; k1 < 64; ++k1)
+    for (int n2 = 0; n2 < 64; ++n2) {
+      const double ang = -2.0 * M_PI * (double)((k1 * n2) % 4096) / 4096.0;
+      tw[k1 * 64 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  std::vector<float> win(2049);
+  for (int n = 0; n <= 2048; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / 4096.0));
+
+  auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload((void**)&p->d_tw, tw.data(), tw.size() * sizeof(float2));
+  if (e == cudaSuccess) e = upload((void**)&p->d_win, win.data(), win.size() * sizeof(float));
+  if (e == cudaSuccess) e = upload((void**)&p->d_band_w, bw.data(), bw.size() * sizeof(float));
+  if (e == cudaSuccess) e = upload((void**)&p->d_band_start, bfirst.data(), bfirst.size() * sizeof(int));
+  if (e == cudaSuccess) e = upload((void**)&p->d_band_ofs, bofs.data(), bofs.size() * sizeof(int));
+  if (e == cudaSuccess && p->frontend_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
+  if (e == cudaSuccess && p->frontend_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
+  if (e != cudaSuccess) {
+    cacfe_plan_destroy(p);
+    return fail(CACFE_ECUDA, "plan_create: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return CACFE_OK;
+}
+
+void cacfe_plan_destroy(cacfe_plan* p) {
+  if (p == nullptr) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_tw);
+  cudaFree(p->d_win);
+  cudaFree(p->d_band_w);
+  cudaFree(p->d_band_start);
+  cudaFree(p->d_band_ofs);
+  delete p;
+}
+
+int cacfe_plan_num_frames(const cacfe_plan* p) { return p ? p->n_frames : fail(CACFE_EINVAL, "null plan"); }
+int cacfe_plan_num_bins(const cacfe_plan* p) { return p ? p->n_bins : fail(CACFE_EINVAL, "null plan"); }
+long long cacfe_plan_launch_count(const cacfe_plan* p) { return p ? p->launches.load() : 0; }
+
+int cacfe_plan_profile(cacfe_plan* p, int enable) {
+  if (!p) return fail(CACFE_EINVAL, "plan_profile: null plan");
+  p->profile = enable != 0;
+  return CACFE_OK;
+}
+
+int cacfe_plan_profile_read(cacfe_plan* p, double* k1_ms, long long* k1_launches) {
+  if (!p || !k1_ms || !k1_launches) return fail(CACFE_EINVAL, "plan_profile_read: null argument");
+  double total = 0.0;
+  for (auto& ev : p->k1_events) {
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventSynchronize(ev.second));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *k1_ms = total;
+  *k1_launches = (long long)p->k1_events.size();
+  p->k1_events.clear();
+  return CACFE_OK;
+}
+
+int cacfe_plan_filterbank(const cacfe_plan* p, float* out) {
+  if (!p || !out) return fail(CACFE_EINVAL, "plan_filterbank: null argument");
+  std::memcpy(out, p->bank.data(), p->bank.size() * sizeof(float));
+  return CACFE_OK;
+}
+
+int cacfe_plan_bin_range(const cacfe_plan* p, int* lo, int* hi) {
+  if (!p || !lo || !hi) return fail(CACFE_EINVAL, "plan_bin_range: null argument");
+  *lo = p->bin_lo;
+  *hi = p->bin_hi;
+  return CACFE_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int pick_splits(const cacfe_plan* p, long long rows) {
+  long long s = (2LL * p->sm_count + rows - 1) / rows;
+  if (s < 1) s = 1;
+  if (s > kMaxSplits) s = kMaxSplits;
+  return (int)s;
+}
+
+struct PcenGrid {
+  int block, gx;
+};
+PcenGrid pcen_grid(long long rows_per_clip) {
+  PcenGrid g;
+  long long blk = ((rows_per_clip + 31) / 32) * 32;
+  g.block = (int)(blk > 256 ? 256 : blk);
+  g.gx = (int)((rows_per_clip + g.block - 1) / g.block);
+  return g;
+}
+
+size_t pcen_ws_bytes(int B, long long rows_per_clip) {
+  const PcenGrid g = pcen_grid(rows_per_clip);
+  return align256((size_t)B * g.gx * sizeof(float2)) + align256((size_t)B * sizeof(float2));
+}
+
+int compress_blocks(long long entries, long long per_entry) {
+  long long want = (per_entry + 4095) / 4096;
+  long long cap = 4096 / (entries < 1 ? 1 : entries);
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+size_t frontend_ws_bytes(int B) { return align256((size_t)B * kMaxSplits * sizeof(float2)); }
+
+int check_launch(cacfe_plan* p, const char* what, int n_launches = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CACFE_ECUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  p->launches.fetch_add(n_launches);
+  return CACFE_OK;
+}
+
+int fill_pcen_args(const cacfe_pcen_params* q, cacfe::PcenArgs& a) {
+  if (!(q->eps > 0.0f)) return fail(CACFE_EINVAL, "pcen: eps must be positive");
+  const float w = fminf(fmaxf(q->smooth, 0.0f), 1.0f);        // tf.clip_by_value(smooth, 0, 1)   tfpcen.py:35
+  const float gain = fminf(q->gain, 1.0f);                     // tfpcen.py:90
+  const float root = fmaxf(q->root, 1.0f);                     // tfpcen.py:91
+  a.w = w;
+  a.one_minus_w = 1.0f - w;
+  a.gain = gain;
+  a.bias = q->bias;
+  a.inv_root = 1.0f / root;
+  a.bias_pow = powf(q->bias, a.inv_root);
+  a.eps = q->eps;
+  a.root_is_2 = (root == 2.0f);
+  return CACFE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t cacfe_pcen_workspace_bytes(int B, long long outer_per_clip, int inner) {
+  return pcen_ws_bytes(B, outer_per_clip * inner);
+}
+
+size_t cacfe_compress_workspace_bytes(long long entries, long long per_entry) {
+  return align256((size_t)entries * compress_blocks(entries, per_entry) * sizeof(cacfe::Stats)) +
+         align256((size_t)entries * sizeof(cacfe::Stats));
+}
+
+size_t cacfe_workspace_bytes(const cacfe_plan* p, int B) {
+  if (!p || B < 1) return 0;
+  const size_t feat = (size_t)p->n_frames * p->cfg.n_mels;
+  size_t need = frontend_ws_bytes(B);
+  need += align256((size_t)B * feat * sizeof(float));                   // mel intermediate of frontend_pcen
+  size_t pc = pcen_ws_bytes(B, p->cfg.n_mels);
+  const size_t pc_img = pcen_ws_bytes(B, (long long)p->cfg.n_mels * p->cfg.channels);
+  if (pc_img > pc) pc = pc_img;
+  size_t cp = cacfe_compress_workspace_bytes(B, (long long)feat * p->cfg.channels);
+  const size_t cp1 = cacfe_compress_workspace_bytes(1, (long long)B * feat * p->cfg.channels);
+  if (cp1 > cp) cp = cp1;
+  return need + (pc > cp ? pc : cp);
+}
+
+int cacfe_normalize(cacfe_plan* p, const float* in, float* out, long long rows, long long n, void* ws, void* stream) {
+  if (!p || !in || !out || !ws) return fail(CACFE_EINVAL, "normalize: null argument");
+  if (rows < 1 || n < 1 || rows > 65535) return fail(CACFE_ESHAPE, "normalize: rows=%lld n=%lld", rows, n);
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = pick_splits(p, rows);
+  if (rows * splits * (long long)sizeof(float2) > (long long)frontend_ws_bytes((int)rows)) splits = 1;
+  float2* partial = (float2*)ws;
+  cacfe::row_minmax_kernel<<<dim3(splits, (unsigned)rows), 256, 0, st>>>(in, n, splits, partial);
+  long long gx = (n + 256 * 8 - 1) / (256 * 8);
+  if (gx > 1024) gx = 1024;
+  cacfe::row_normalize_kernel<<<dim3((unsigned)gx, (unsigned)rows), 256, 0, st>>>(in, out, n, splits, partial);
+  return check_launch(p, "normalize", 2);
+}
+
+static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, int layout, int channels, void* ws,
+                           cudaStream_t st) {
+  if (!p->frontend_ok)
+    return fail(CACFE_EINVAL, "frontend: the fused kernel is built for n_fft=4096 (got %d) and needs %zu B of shared memory",
+                p->cfg.n_fft, p->k1.total);
+  cacfe::FrontendArgs a;
+  int launches = 1;
+  a.partial = nullptr;
+  a.splits = 1;
+  if (p->cfg.normalize) {
+    a.splits = pick_splits(p, B);
+    a.partial = (const float2*)ws;
+    cacfe::row_minmax_kernel<<<dim3(a.splits, B), 256, 0, st>>>(raw, p->cfg.n_samples, a.splits, (float2*)ws);
+    launches = 2;
+  }
+  a.in = raw;
+  a.out = feat;
+  a.tw = p->d_tw;
+  a.win = p->d_win;
+  a.band_w = p->d_band_w;
+  a.band_start = p->d_band_start;
+  a.band_ofs = p->d_band_ofs;
+  a.n_samples = p->cfg.n_samples;
+  a.hop = p->cfg.hop;
+  a.n_frames = p->n_frames;
+  a.n_mels = p->cfg.n_mels;
+  a.nnz = p->nnz;
+  a.origin = p->origin;
+  a.reflect = p->cfg.framing == CACFE_FRAME_CENTER_REFLECT;
+  a.power = p->cfg.power;
+  a.channels = channels;
+  a.layout = layout;
+  a.bin_lo = p->bin_lo;
+  a.bin_hi = p->bin_hi;
+  a.tiles_per_clip = (p->n_frames + cacfe::kTileFrames - 1) / cacfe::kTileFrames;
+  const long long grid = (long long)B * a.tiles_per_clip;
+  if (grid > 2147483647LL) return fail(CACFE_ESHAPE, "frontend: batch too large for one launch");
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (p->profile) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
+  if (p->nq <= 15)
+    cacfe::stft_mel_kernel<15><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
+  else
+    cacfe::stft_mel_kernel<33><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
+  if (p->profile) {
+    cudaEventRecord(ev1, st);
+    p->k1_events.emplace_back(ev0, ev1);
+  }
+  return check_launch(p, "frontend", launches);
+}
+
+int cacfe_frontend(cacfe_plan* p, const float* raw, float* feat, int B, void* ws, void* stream) {
+  if (!p || !raw || !feat) return fail(CACFE_EINVAL, "frontend: null argument");
+  if (p->cfg.normalize && !ws) return fail(CACFE_EINVAL, "frontend: workspace required when normalize=1");
+  if (B < 1 || B > 65535) return fail(CACFE_ESHAPE, "frontend: B=%d out of range [1, 65535]", B);
+  if ((reinterpret_cast<uintptr_t>(raw) & 3) || (reinterpret_cast<uintptr_t>(feat) & 3))
+    return fail(CACFE_EALIGN, "frontend: buffers must be 4-byte aligned");
+  CUDA_TRY(cudaSetDevice(p->device));
+  return launch_frontend(p, raw, feat, B, p->cfg.out_layout, p->cfg.channels, ws, (cudaStream_t)stream);
+}
+
+int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, int B, int T, void* stream) {
+  if (!p || !spec || !feat) return fail(CACFE_EINVAL, "mel_from_spectrogram: null argument");
+  if (B < 1 || B > 65535 || T < 1) return fail(CACFE_ESHAPE, "mel_from_spectrogram: B=%d T=%d", B, T);
+  CUDA_TRY(cudaSetDevice(p->device));
+  cacfe::MelSpecArgs a;
+  a.spec = spec;
+  a.out = feat;
+  a.band_w = p->d_band_w;
+  a.band_start = p->d_band_start;
+  a.band_ofs = p->d_band_ofs;
+  a.n_bins = p->n_bins;
+  a.T = T;
+  a.n_mels = p->cfg.n_mels;
+  a.nnz = p->nnz;
+  a.bin_lo = p->bin_lo;
+  a.power = p->cfg.power;
+  a.channels = p->cfg.channels;
+  a.layout = p->cfg.out_layout;
+  const size_t smem = sizeof(float) * ((p->nnz + 3) & ~3) + sizeof(int) * (2 * p->cfg.n_mels + 1);
+  if (smem > 48 * 1024) return fail(CACFE_EINVAL, "mel_from_spectrogram: filterbank too dense for the banded kernel");
+  dim3 grid((T + cacfe::kMelSpecThreads - 1) / cacfe::kMelSpecThreads, B);
+  cacfe::melspec_banded_kernel<<<grid, cacfe::kMelSpecThreads, smem, (cudaStream_t)stream>>>(a);
+  return check_launch(p, "mel_from_spectrogram");
+}
+
+int cacfe_ema(cacfe_plan* p, float smooth, const float* in, float* out, int B, long long outer_per_clip, int T, int inner,
+              void* stream) {
+  if (!p || !in || !out) return fail(CACFE_EINVAL, "ema: null argument");
+  if (in == out) return fail(CACFE_EINVAL, "ema: in-place operation is not supported");
+  if (B < 1 || B > 65535 || T < 1 || inner < 1 || outer_per_clip < 1) return fail(CACFE_ESHAPE, "ema: bad shape");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cacfe::PcenArgs a{};
+  a.in = in;
+  a.out = out;
+  a.T = T;
+  a.inner = inner;
+  a.rows_per_clip = (int)(outer_per_clip * inner);
+  a.w = fminf(fmaxf(smooth, 0.0f), 1.0f);
+  a.one_minus_w = 1.0f - a.w;
+  const PcenGrid g = pcen_grid(a.rows_per_clip);
+  cacfe::ema_kernel<<<dim3(g.gx, B), g.block, 0, (cudaStream_t)stream>>>(a);
+  return check_launch(p, "ema");
+}
+
+static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* in, float* out, int B,
+                       long long outer_per_clip, int T, int inner, void* ws, cudaStream_t st) {
+  cacfe::PcenArgs a{};
+  int rc = fill_pcen_args(q, a);
+  if (rc != CACFE_OK) return rc;
+  a.in = in;
+  a.out = out;
+  a.T = T;
+  a.inner = inner;
+  a.rows_per_clip = (int)(outer_per_clip * inner);
+  const PcenGrid g = pcen_grid(a.rows_per_clip);
+  dim3 grid(g.gx, B);
+  if (q->norm_scope == CACFE_NORM_NONE) {
+    cacfe::pcen_kernel<cacfe::PCEN_RAW><<<grid, g.block, 0, st>>>(a);
+    return check_launch(p, "pcen");
+  }
+  if (!ws) return fail(CACFE_EINVAL, "pcen: workspace required for the min-max scope");
+  float2* partial = (float2*)ws;
+  float2* extremes = (float2*)((char*)ws + align256((size_t)B * g.gx * sizeof(float2)));
+  a.partial = partial;
+  a.extremes = extremes;
+  a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
+  cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<grid, g.block, 0, st>>>(a);
+  if (a.per_clip_extremes)
+    cacfe::minmax_finalize_kernel<<<B, 256, 0, st>>>(partial, g.gx, extremes);
+  else
+    cacfe::minmax_finalize_kernel<<<1, 256, 0, st>>>(partial, B * g.gx, extremes);
+  cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<grid, g.block, 0, st>>>(a);
+  return check_launch(p, "pcen", 3);
+}
+
+int cacfe_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* in, float* out, int B, long long outer_per_clip,
+               int T, int inner, void* ws, void* stream) {
+  if (!p || !q || !in || !out) return fail(CACFE_EINVAL, "pcen: null argument");
+  if (in == out) return fail(CACFE_EINVAL, "pcen: in-place operation is not supported");
+  if (B < 1 || B > 65535 || T < 1 || inner < 1 || outer_per_clip < 1 || outer_per_clip * inner > 2147483647LL)
+    return fail(CACFE_ESHAPE, "pcen: bad shape");
+  if (q->norm_scope < 0 || q->norm_scope > 2) return fail(CACFE_EINVAL, "pcen: unknown norm_scope");
+  CUDA_TRY(cudaSetDevice(p->device));
+  return launch_pcen(p, q, in, out, B, outer_per_clip, T, inner, ws, (cudaStream_t)stream);
+}
+
+int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float* out, long long entries,
+                   long long per_entry, void* ws, void* stream) {
+  if (!p || !in || !out) return fail(CACFE_EINVAL, "compress: null argument");
+  if (in == out) return fail(CACFE_EINVAL, "compress: in-place operation is not supported");
+  if (entries < 1 || entries > 65535 || per_entry < 1) return fail(CACFE_ESHAPE, "compress: bad shape");
+  if (mode < 0 || mode > 3) return fail(CACFE_EINVAL, "compress: unknown mode %d", mode);
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compress_blocks(entries, per_entry);
+  dim3 grid(blocks, (unsigned)entries);
+  int launches = 1;
+  cacfe::Stats* stats = nullptr;
+  if (mode != CACFE_COMPRESS_MAG_POW) {
+    if (!ws) return fail(CACFE_EINVAL, "compress: workspace required for this mode");
+    cacfe::Stats* partial = (cacfe::Stats*)ws;
+    stats = (cacfe::Stats*)((char*)ws + align256((size_t)entries * blocks * sizeof(cacfe::Stats)));
+    cacfe::stats_kernel<<<grid, 256, 0, st>>>(in, per_entry, partial);
+    cacfe::stats_finalize_kernel<<<(unsigned)entries, 32, 0, st>>>(partial, blocks, stats);
+    launches = 3;
+  }
+  switch (mode) {
+    case CACFE_COMPRESS_MAG_POW:
+      cacfe::compress_kernel<cacfe::COMPRESS_MAG_POW><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
+      break;
+    case CACFE_COMPRESS_POWER_TO_DB:
+      cacfe::compress_kernel<cacfe::COMPRESS_POWER_TO_DB><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
+      break;
+    case CACFE_COMPRESS_MINMAX:
+      cacfe::compress_kernel<cacfe::COMPRESS_MINMAX><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
+      break;
+    default:
+      cacfe::compress_kernel<cacfe::COMPRESS_STD><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
+      break;
+  }
+  return check_launch(p, "compress", launches);
+}
+
+int cacfe_frontend_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* raw, float* out, int B, void* ws,
+                        void* stream) {
+  if (!p || !q || !raw || !out || !ws) return fail(CACFE_EINVAL, "frontend_pcen: null argument");
+  if (B < 1 || B > 65535) return fail(CACFE_ESHAPE, "frontend_pcen: B=%d out of range", B);
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  void* ws_front = w;
+  float* mel = (float*)(w + frontend_ws_bytes(B));
+  void* ws_pcen = w + frontend_ws_bytes(B) + align256((size_t)B * p->n_frames * p->cfg.n_mels * sizeof(float));
+  int rc = launch_frontend(p, raw, mel, B, CACFE_LAYOUT_BTM, 1, ws_front, st);
+  if (rc != CACFE_OK) return rc;
+  return launch_pcen(p, q, mel, out, B, 1, p->n_frames, p->cfg.n_mels, ws_pcen, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer pipeline
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct cacfe_hostpipe {
+  cacfe_plan* plan = nullptr;
+  int max_B = 0, chunk = 0;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaEvent_t all_reduced = nullptr;
+  float* d_in[2] = {nullptr, nullptr};   // [chunk][n_samples]
+  float* d_feat = nullptr;               // [max_B] mel features (layout of the run)
+  float* d_out[2] = {nullptr, nullptr};  // [chunk] PCEN output staging
+  void* d_ws[2] = {nullptr, nullptr};    // per-stream front-end workspace
+  float2* d_partial = nullptr;           // [max_B][gx]
+  float2* d_extremes = nullptr;          // [max_B]
+  size_t bytes = 0;
+};
+
+extern "C" {
+
+void cacfe_hostpipe_destroy(cacfe_hostpipe* h) {
+  if (!h) return;
+  cudaSetDevice(h->plan->device);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stream[i]) cudaStreamSynchronize(h->stream[i]);
+    cudaFree(h->d_in[i]);
+    cudaFree(h->d_out[i]);
+    cudaFree(h->d_ws[i]);
+    if (h->done[i]) cudaEventDestroy(h->done[i]);
+    if (h->stream[i]) cudaStreamDestroy(h->stream[i]);
+  }
+  if (h->all_reduced) cudaEventDestroy(h->all_reduced);
+  cudaFree(h->d_feat);
+  cudaFree(h->d_partial);
+  cudaFree(h->d_extremes);
+  delete h;
+}
+
+int cacfe_hostpipe_create(cacfe_plan* p, int max_B, int chunk, cacfe_hostpipe** out) {
+  if (!p || !out) return fail(CACFE_EINVAL, "hostpipe_create: null argument");
+  *out = nullptr;
+  if (max_B < 1 || max_B > 65535 || chunk < 1) return fail(CACFE_ESHAPE, "hostpipe_create: max_B=%d chunk=%d", max_B, chunk);
+  if (chunk > max_B) chunk = max_B;
+  CUDA_TRY(cudaSetDevice(p->device));
+  cacfe_hostpipe* h = new cacfe_hostpipe();
+  h->plan = p;
+  h->max_B = max_B;
+  h->chunk = chunk;
+  const size_t feat_clip = (size_t)p->n_frames * p->cfg.n_mels * p->cfg.channels * sizeof(float);
+  const size_t pcen_clip = (size_t)p->n_frames * p->cfg.n_mels * sizeof(float);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) {
+    if (e == cudaSuccess) {
+      e = cudaMalloc(ptr, bytes);
+      if (e == cudaSuccess) h->bytes += bytes;
+    }
+  };
+  for (int i = 0; i < 2; ++i) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming);
+    alloc((void**)&h->d_in[i], (size_t)chunk * p->cfg.n_samples * sizeof(float));
+    alloc((void**)&h->d_out[i], (size_t)chunk * pcen_clip);
+    alloc(&h->d_ws[i], frontend_ws_bytes(chunk));
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->all_reduced, cudaEventDisableTiming);
+  alloc((void**)&h->d_feat, (size_t)max_B * (feat_clip > pcen_clip ? feat_clip : pcen_clip));
+  alloc((void**)&h->d_partial, (size_t)max_B * pcen_grid(p->cfg.n_mels).gx * sizeof(float2));
+  alloc((void**)&h->d_extremes, (size_t)max_B * sizeof(float2));
+  if (e != cudaSuccess) {
+    cacfe_hostpipe_destroy(h);
+    return fail(e == cudaErrorMemoryAllocation ? CACFE_ENOMEM : CACFE_ECUDA, "hostpipe_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return CACFE_OK;
+}
+
+size_t cacfe_hostpipe_device_bytes(const cacfe_hostpipe* h) { return h ? h->bytes : 0; }
+
+int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const float* host_in, float* host_out, int B) {
+  if (!h || !host_in || !host_out) return fail(CACFE_EINVAL, "hostpipe_run: null argument");
+  if (B < 1 || B > h->max_B) return fail(CACFE_ESHAPE, "hostpipe_run: B=%d exceeds max_B=%d", B, h->max_B);
+  cacfe_plan* p = h->plan;
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int ns = p->cfg.n_samples;
+  const int nchunks = (B + h->chunk - 1) / h->chunk;
+  if (q == nullptr) {
+    // mel image only: every chunk is independent -> H2D / kernels / D2H fully pipelined on two streams
+    const size_t feat_clip = (size_t)p->n_frames * p->cfg.n_mels * p->cfg.channels;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
+      cudaStream_t st = h->stream[s];
+      CUDA_TRY(cudaMemcpyAsync(h->d_in[s], host_in + (size_t)b0 * ns, (size_t)nb * ns * sizeof(float),
+                               cudaMemcpyHostToDevice, st));
+      float* feat = h->d_feat + (size_t)b0 * feat_clip;
+      int rc = launch_frontend(p, h->d_in[s], feat, nb, p->cfg.out_layout, p->cfg.channels, h->d_ws[s], st);
+      if (rc != CACFE_OK) return rc;
+      CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)b0 * feat_clip, feat, (size_t)nb * feat_clip * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->stream[1]));
+    return CACFE_OK;
+  }
+  if (q->norm_scope < 0 || q->norm_scope > 2) return fail(CACFE_EINVAL, "hostpipe_run: unknown norm_scope");
+  cacfe::PcenArgs a{};
+  int rc = fill_pcen_args(q, a);
+  if (rc != CACFE_OK) return rc;
+  const int T = p->n_frames, M = p->cfg.n_mels;
+  const size_t clip = (size_t)T * M;
+  const PcenGrid g = pcen_grid(M);
+  a.T = T;
+  a.inner = M;
+  a.rows_per_clip = M;
+  a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
+  a.extremes = h->d_extremes;
+  const bool global = q->norm_scope == CACFE_NORM_TENSOR;
+  // phase 1: per chunk H2D -> min/max -> mel [b][T][M] (device resident) -> PCEN reduce (or the final PCEN
+  // when the scope allows the chunk to finish on its own)
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
+    cudaStream_t st = h->stream[s];
+    CUDA_TRY(cudaMemcpyAsync(h->d_in[s], host_in + (size_t)b0 * ns, (size_t)nb * ns * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    float* mel = h->d_feat + (size_t)b0 * clip;
+    rc = launch_frontend(p, h->d_in[s], mel, nb, CACFE_LAYOUT_BTM, 1, h->d_ws[s], st);
+    if (rc != CACFE_OK) return rc;
+    cacfe::PcenArgs ac = a;
+    ac.in = mel;
+    ac.out = h->d_out[s];
+    ac.partial = h->d_partial + (size_t)b0 * g.gx;
+    ac.extremes = h->d_extremes + b0;
+    if (q->norm_scope == CACFE_NORM_NONE) {
+      cacfe::pcen_kernel<cacfe::PCEN_RAW><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+    } else {
+      cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      if (!global) {
+        cacfe::minmax_finalize_kernel<<<nb, 256, 0, st>>>(ac.partial, g.gx, h->d_extremes + b0);
+        cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      }
+    }
+    if ((rc = check_launch(p, "hostpipe", global ? 1 : (q->norm_scope == CACFE_NORM_NONE ? 1 : 3))) != CACFE_OK) return rc;
+    if (!global)
+      CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)b0 * clip, h->d_out[s], (size_t)nb * clip * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(h->done[s], st));
+  }
+  if (global) {
+    // phase 2: tensor-global extremes need every chunk (tfpcen.py:105-110)
+    CUDA_TRY(cudaStreamWaitEvent(h->stream[0], h->done[1], 0));
+    cacfe::minmax_finalize_kernel<<<1, 256, 0, h->stream[0]>>>(h->d_partial, B * g.gx, h->d_extremes);
+    if ((rc = check_launch(p, "hostpipe")) != CACFE_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->all_reduced, h->stream[0]));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream[1], h->all_reduced, 0));
+    // phase 3: apply + D2H per chunk, alternating streams
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
+      cudaStream_t st = h->stream[s];
+      cacfe::PcenArgs ac = a;
+      ac.in = h->d_feat + (size_t)b0 * clip;
+      ac.out = h->d_out[s];
+      ac.extremes = h->d_extremes;
+      ac.per_clip_extremes = 0;
+      cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      if ((rc = check_launch(p, "hostpipe")) != CACFE_OK) return rc;
+      CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)b0 * clip, h->d_out[s], (size_t)nb * clip * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
+  CUDA_TRY(cudaStreamSynchronize(h->stream[1]));
+  return CACFE_OK;
+}
+
+int cacfe_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(CACFE_EINVAL, "host_register: null argument");
+  CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CACFE_OK;
+}
+
+int cacfe_host_unregister(void* ptr) {
+  if (!ptr) return fail(CACFE_EINVAL, "host_unregister: null argument");
+  CUDA_TRY(cudaHostUnregister(ptr));
+  return CACFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DLPack
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+// dlpack.h v0.8 ABI (stable since v0.2): only the fields read here.
+struct DLDevice { int32_t device_type; int32_t device_id; };
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;
+  uint64_t byte_offset;
+};
+struct DLManagedTensorABI {
+  DLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(DLManagedTensorABI*);
+};
+constexpr int kDLCUDA = 2, kDLFloat = 2;
+
+int dl_check(const cacfe_plan* p, const DLManagedTensorABI* m, const char* what, const DLTensor** out) {
+  if (!m) return fail(CACFE_EINVAL, "%s: null DLManagedTensor", what);
+  const DLTensor& t = m->dl_tensor;
+  if (t.device.device_type != kDLCUDA) return fail(CACFE_EDEVICE, "%s: tensor is not on a CUDA device", what);
+  if (t.device.device_id != p->device)
+    return fail(CACFE_EDEVICE, "%s: tensor on cuda:%d, plan on cuda:%d", what, t.device.device_id, p->device);
+  if (t.dtype.code != kDLFloat || t.dtype.bits != 32 || t.dtype.lanes != 1) return fail(CACFE_EDTYPE, "%s: float32 required", what);
+  if (t.strides) {
+    int64_t expect = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+      if (t.shape[i] != 1 && t.strides[i] != expect) return fail(CACFE_ESHAPE, "%s: tensor must be C-contiguous", what);
+      expect *= t.shape[i];
+    }
+  }
+  *out = &t;
+  return CACFE_OK;
+}
+float* dl_ptr(const DLTensor* t) { return (float*)((char*)t->data + t->byte_offset); }
+int64_t dl_numel(const DLTensor* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+  return n;
+}
+}  // namespace
+
+extern "C" {
+
+int cacfe_frontend_dlpack(cacfe_plan* p, struct DLManagedTensor* raw_, struct DLManagedTensor* feat_, void* ws, void* stream) {
+  if (!p) return fail(CACFE_EINVAL, "frontend_dlpack: null plan");
+  const DLTensor *raw, *feat;
+  int rc;
+  if ((rc = dl_check(p, (const DLManagedTensorABI*)raw_, "frontend_dlpack(raw)", &raw)) != CACFE_OK) return rc;
+  if ((rc = dl_check(p, (const DLManagedTensorABI*)feat_, "frontend_dlpack(feat)", &feat)) != CACFE_OK) return rc;
+  if (raw->ndim != 2 || raw->shape[1] != p->cfg.n_samples)
+    return fail(CACFE_ESHAPE, "frontend_dlpack: raw must be [B][%d]", p->cfg.n_samples);
+  const int64_t B = raw->shape[0];
+  const int64_t want = B * p->n_frames * p->cfg.n_mels * p->cfg.channels;
+  if (dl_numel(feat) != want) return fail(CACFE_ESHAPE, "frontend_dlpack: feat has %lld elements, expected %lld",
+                                          (long long)dl_numel(feat), (long long)want);
+  return cacfe_frontend(p, dl_ptr(raw), dl_ptr(feat), (int)B, ws, stream);
+}
+
+int cacfe_pcen_dlpack(cacfe_plan* p, const cacfe_pcen_params* q, struct DLManagedTensor* in_, struct DLManagedTensor* out_,
+                      void* ws, void* stream) {
+  if (!p) return fail(CACFE_EINVAL, "pcen_dlpack: null plan");
+  const DLTensor *in, *out;
+  int rc;
+  if ((rc = dl_check(p, (const DLManagedTensorABI*)in_, "pcen_dlpack(in)", &in)) != CACFE_OK) return rc;
+  if ((rc = dl_check(p, (const DLManagedTensorABI*)out_, "pcen_dlpack(out)", &out)) != CACFE_OK) return rc;
+  if (in->ndim != 3) return fail(CACFE_ESHAPE, "pcen_dlpack: [batch, time, filters] required (tfpcen.py:34)");
+  if (dl_numel(in) != dl_numel(out)) return fail(CACFE_ESHAPE, "pcen_dlpack: in/out sizes differ");
+  return cacfe_pcen(p, q, dl_ptr(in), dl_ptr(out), (int)in->shape[0], 1, (int)in->shape[1], (int)in->shape[2], ws, stream);
+}
+
+}  // extern "C"

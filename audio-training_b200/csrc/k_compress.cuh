@@ -1,0 +1,126 @@
+// Point-wise compression / normalisation epilogues with a tensor- or clip-wide statistic, sm_100a.
+//
+//   MINMAX       normalize_minmax  tfpcen.py:105-110, tfdataset.py:1897-1902    2*((x-min)/(max-min)) - 1
+//   POWER_TO_DB  power_to_db       tfdataset.py:1906-1913 (== librosa.power_to_db(ref=np.max), predict_utils.py:216)
+//   STD          normalize_std     tfdataset.py:1883-1893                        (x-mean)/(std + 1e-7)
+//   MAG_POW      MagTransform      badwinner2.py:32-49                           x ** sigmoid(a)   (no statistic)
+//
+// The tensor is a flat run of `per_entry` floats per scope entry (1 entry = whole tensor, or B = per clip).
+// Pass 1 (stats_kernel) writes block partials, stats_finalize_kernel folds them, pass 2 applies.  HBM bound.
+#pragma once
+#include "cacfe_common.cuh"
+
+namespace cacfe {
+
+enum : int { COMPRESS_MAG_POW = 0, COMPRESS_POWER_TO_DB = 1, COMPRESS_MINMAX = 2, COMPRESS_STD = 3 };
+
+struct Stats {  // one per scope entry
+  float mn, mx;
+  double sum, sumsq;
+};
+
+// grid = (blocks_per_entry, entries), block = 256
+__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ in, long long per_entry,
+                                                    Stats* __restrict__ partial) {
+  __shared__ float scratch[64];
+  __shared__ double dscratch[16];
+  const float* x = in + (size_t)blockIdx.y * per_entry;
+  float mn = INFINITY, mx = -INFINITY;
+  double s = 0.0, ss = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_entry; i += stride) {
+    const float v = ld_stream(x + i);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+    s += (double)v;
+    ss += (double)v * (double)v;
+  }
+  block_minmax(mn, mx, scratch);
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    dscratch[warp] = s;
+    dscratch[8 + warp] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += dscratch[w];
+      b += dscratch[8 + w];
+    }
+    Stats st;
+    st.mn = mn;
+    st.mx = mx;
+    st.sum = a;
+    st.sumsq = b;
+    partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = st;
+  }
+}
+
+// grid = entries, block = 32
+__global__ void stats_finalize_kernel(const Stats* __restrict__ partial, int per_entry_blocks, Stats* __restrict__ out) {
+  const Stats* p = partial + (size_t)blockIdx.x * per_entry_blocks;
+  float mn = INFINITY, mx = -INFINITY;
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < per_entry_blocks; i += 32) {
+    mn = fminf(mn, p[i].mn);
+    mx = fmaxf(mx, p[i].mx);
+    s += p[i].sum;
+    ss += p[i].sumsq;
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (threadIdx.x == 0) {
+    Stats st;
+    st.mn = mn;
+    st.mx = mx;
+    st.sum = s;
+    st.sumsq = ss;
+    out[blockIdx.x] = st;
+  }
+}
+
+// grid = (blocks_per_entry, entries), block = 256
+template <int MODE>
+__global__ void __launch_bounds__(256) compress_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                       long long per_entry, float param,
+                                                       const Stats* __restrict__ stats) {
+  const float* x = in + (size_t)blockIdx.y * per_entry;
+  float* y = out + (size_t)blockIdx.y * per_entry;
+  float c0 = 0.0f, c1 = 0.0f;
+  if (MODE == COMPRESS_MINMAX) {
+    const Stats st = stats[blockIdx.y];
+    c0 = st.mn;
+    c1 = st.mx - st.mn;
+  } else if (MODE == COMPRESS_POWER_TO_DB) {
+    const Stats st = stats[blockIdx.y];
+    c0 = 10.0f * log10f(fmaxf(1e-10f, st.mx));  // 10 log10(max(amin, ref)); max of the dB image is exactly 0
+  } else if (MODE == COMPRESS_STD) {
+    const Stats st = stats[blockIdx.y];
+    const double mean = st.sum / (double)per_entry;
+    const double var = fmax(st.sumsq / (double)per_entry - mean * mean, 0.0);
+    c0 = (float)mean;
+    c1 = (float)sqrt(var) + 1e-7f;  // keras.backend.epsilon()
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_entry; i += stride) {
+    const float v = ld_stream(x + i);
+    float r;
+    if (MODE == COMPRESS_MAG_POW) {
+      r = exp2f(param * log2f(v));  // v ** param for v >= 0 (0 -> 0, like tf.pow)
+    } else if (MODE == COMPRESS_POWER_TO_DB) {
+      r = fmaxf(10.0f * log10f(fmaxf(1e-10f, v)) - c0, -80.0f);
+    } else if (MODE == COMPRESS_MINMAX) {
+      r = 2.0f * ((v - c0) / c1) - 1.0f;
+    } else {
+      r = (v - c0) / c1;
+    }
+    y[i] = r;
+  }
+}
+
+}  // namespace cacfe

@@ -1,0 +1,94 @@
+"""Drop-in for the reference's `tfpcen` module (tfpcen.py:8-110): ExponentialMovingAverage, PCEN, normalize_minmax.
+
+The layers keep the reference's constructor arguments, weight names, creation order and initial values so
+checkpoints map one to one; `__call__` runs the CUDA kernels (forward only -- the front-end is used frozen).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _runtime as rt
+
+
+def _plan(device):
+    return rt.get_plan(rt.FrontendConfig(), device)
+
+
+class ExponentialMovingAverage:
+    """tfpcen.py:8-39.  call(inputs[batch, seq, filters], initial_state): M[t] = w x[t] + (1-w) M[t-1] with
+    w = clip(smooth, 0, 1).  As at the reference's only call site (tfpcen.py:92) the initial state is inputs[:, 0, :]."""
+
+    def __init__(self, coeff_init, trainable=False):
+        self.name = "EMA"
+        self._coeff_init = coeff_init
+        self._trainable = trainable
+        self._weights = np.full([1], coeff_init, dtype=np.float32)  # weight name 'smooth'
+
+    @property
+    def weights(self):
+        return {"smooth": self._weights}
+
+    def call(self, inputs, initial_state=None, time_axis=1):
+        t, restore = rt.to_device(inputs)
+        if initial_state is not None:
+            first, _ = rt.to_device(initial_state)
+            if not bool((first == t.select(time_axis, 0)).all()):
+                raise NotImplementedError("ExponentialMovingAverage: only initial_state = inputs[:, 0] is built "
+                                          "(the reference's only use, tfpcen.py:92)")
+        return restore(_plan(t.device.index).ema(t, float(self._weights[0]), time_axis))
+
+    __call__ = call
+
+
+class PCEN:
+    """tfpcen.py:42-99.  Weights in creation order: gain 0.98, bias 2.0, root 2.0, EMA/smooth 0.04, a-power -1.0
+    (declared and never used by call, Q12).  Input contract: rank 3 [batch, time, filters]; a rank-4 image
+    [batch, mels, time, channels] (how audiomodel.py:793 attaches the layer, Q13) is handled as our documented
+    extension: the smoother runs along the time axis of every (mel, channel) row.
+
+    norm_scope: "tensor" = the reference's tensor-global min-max (tfpcen.py:105-110); "clip" / "none" are ours."""
+
+    serial_key = "MyLayers>PCEN"  # the reference registers this class under MagTransform's key (Q12); we do not
+
+    def __init__(self, norm_scope="tensor", **kwargs):
+        self.name = kwargs.get("name", "pcen")
+        self.gain = np.full([1], 0.98, dtype=np.float32)
+        self.bias = np.full([1], 2.0, dtype=np.float32)
+        self.root = np.full([1], 2.0, dtype=np.float32)
+        self.eps = 1e-6
+        self.ema = ExponentialMovingAverage(coeff_init=0.04, trainable=True)
+        self.a = np.full([1], -1.0, dtype=np.float32)  # 'a-power'
+        self.norm_scope = norm_scope
+
+    def state_dict(self):
+        return {"gain": self.gain.copy(), "bias": self.bias.copy(), "root": self.root.copy(),
+                "EMA/smooth": self.ema._weights.copy(), "a-power": self.a.copy()}
+
+    def load_state_dict(self, state):
+        self.gain[:] = state["gain"]
+        self.bias[:] = state["bias"]
+        self.root[:] = state["root"]
+        self.ema._weights[:] = state["EMA/smooth"]
+        if "a-power" in state:
+            self.a[:] = state["a-power"]
+
+    def params(self):
+        return rt.pcen_params(self.gain[0], self.bias[0], self.root[0], self.ema._weights[0], self.eps, self.norm_scope)
+
+    def call(self, inputs):
+        t, restore = rt.to_device(inputs)
+        if t.dim() == 3:
+            axis = 1
+        elif t.dim() == 4:
+            axis = 2
+        else:
+            raise ValueError("PCEN: expected [batch, time, filters] (or the rank-4 image extension)")
+        return restore(_plan(t.device.index).pcen(t, self.params(), axis))
+
+    __call__ = call
+
+
+def normalize_minmax(data):
+    """tfpcen.py:105-110: 2 * ((x - min) / (max - min)) - 1 with min/max over the whole tensor."""
+    t, restore = rt.to_device(data)
+    return restore(_plan(t.device.index).compress(t, "minmax"))

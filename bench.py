@@ -1,0 +1,286 @@
+#!/usr/bin/env python3
+"""Headline benchmark: clips/s for 3 s @ 48 kHz clips -> normalise -> STFT -> mel -> PCEN (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one pass of the hot path over one batch of B synthetic clips (BASELINE.json configs[1]: B = 4096 on one
+B200).  With N > 1 (torchrun, one rank per GPU) every rank processes its own B clips -- clips are independent, no
+collective on the data path -- and `value` is all ranks' clips over the slowest rank's time ("weak" scaling).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (fused STFT/power/mel), algorithmic bytes per launch / its CUDA-event duration
+                measured inside the timed region, against MEASURED_PEAKS.json hbm_gbs; `fp32` gives the roof
+                that actually binds it (the FFT is FP32-issue bound, not HBM bound)
+  cpu_baseline  the oracle's port of the reference's own CPU op order (f32, scipy pocketfft, all host threads) on
+                a bounded sample of the same workload
+  e2e           same metric through the host-buffer API (cacfe_hostpipe: pinned host in -> H2D -> kernels -> D2H)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+CLIP = 144000
+T_FRAMES, N_MELS = 513, 160
+BYTES_PER_CLIP = CLIP * 4 + T_FRAMES * N_MELS * 4          # 904 320 B  (path A fused, 1 channel / BTM)
+FLOPS_PER_CLIP = 68e6                                       # FFT 63.0 M + window/power 5.25 M + banded mel
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12           # 74.4
+METRIC = "clips/sec (3 s @48 kHz -> mel+PCEN)"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()  # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_on_device(torch, B, device, seed):
+    """SURVEY 8d generator shape (noise + 3 linear chirps + DC) evaluated on the device, in chunks."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((B, CLIP), dtype=torch.float32, device=device)
+    t = torch.arange(CLIP, device=device, dtype=torch.float64) / 48000.0
+    for b0 in range(0, B, 256):
+        nb = min(256, B - b0)
+        x = 0.3 * (2.0 * torch.rand((nb, CLIP), generator=g, device=device) - 1.0)
+        p = torch.rand((nb, 3, 3), generator=g, device=device, dtype=torch.float64)
+        for j in range(3):
+            a = 0.05 + 0.45 * p[:, j, 0:1]
+            f0 = 300.0 + 10700.0 * p[:, j, 1:2]
+            f1 = 300.0 + 10700.0 * p[:, j, 2:3]
+            c = (f1 - f0) / 3.0
+            phase = 2.0 * np.pi * (f0 * t[None] + 0.5 * c * t[None] ** 2)
+            x += (a * torch.sin(phase)).float()
+        x += (0.2 * torch.rand((nb, 1), generator=g, device=device) - 0.1)
+        out[b0:b0 + nb] = x
+    return out
+
+
+def cpu_reference_run(n_clips, budget_s, min_batches=3):
+    """The reference's CPU op order (oracle port, f32) on batches of `n_clips` synthetic clips."""
+    from oracle import frontend_oracle as fo
+    w = fo.mel_f(48000, 160, 100, 11000, 4096, 1000)
+    x = fo.synth_clips(np.arange(n_clips))
+    fo.reference_cpu_path(x, w)  # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_batches or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        fo.reference_cpu_path(x, w)
+        times.append(time.perf_counter() - t0)
+    return n_clips / float(np.median(times)), len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n = 32
+    from oracle import frontend_oracle as fo
+    w = fo.mel_f(48000, 160, 100, 11000, 4096, 1000)
+    x = fo.synth_clips(np.arange(n))
+    for _ in range(max(1, min(args.warmup, 2))):
+        fo.reference_cpu_path(x, w)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fo.reference_cpu_path(x, w)
+    dt = (time.perf_counter() - t0) / steps
+    value = n / dt
+    sample = f"{n} synthetic clips per step (BASELINE.json configs[0]); oracle port of the reference op order, f32, scipy pocketfft workers={cores}, numpy sgemm; TensorFlow/librosa are not installable offline"
+    line = {"metric": METRIC, "value": value, "unit": "clips/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "normalize -> STFT 4096/281 pad_end -> |z|^2 -> mel 160 -> PCEN, 32 clips x 3 s @ 48 kHz per step (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import audio_training_b200 as atb
+    from audio_training_b200 import _runtime as rt
+    from audio_training_b200 import distributed as dist_
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    rank, world, local = dist_.init()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    B = args.batch
+    peaks, peak_kind = measured_peaks()
+
+    cfg = rt.FrontendConfig(normalize=True, channels=1, out_layout="btm")
+    plan = rt.get_plan(cfg, local)
+    params = rt.pcen_params()
+    x = synth_on_device(torch, B, device, 20240 + rank)
+    out = torch.empty((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, device=device)
+    plan.workspace_for(B)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        plan.frontend_pcen(x, params, out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plan.profile(True)
+    plan.profile_read()
+    launches0 = plan.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        plan.frontend_pcen(x, params, out)   # inputs (2.36 GB at B=4096) far exceed the 126 MB L2: no flush needed
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = plan.launch_count() - launches0
+    k1_ms, k1_n = plan.profile_read()
+    plan.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = dist_.max_over_ranks(ms_total / args.steps, device)
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel, from the in-region CUDA events --------------------------------------
+    k1_avg_ms = k1_ms / max(k1_n, 1)
+    achieved = BYTES_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e9
+    fp32_achieved = FLOPS_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e12
+    roofline = {"kernel": "stft_mel_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "ms_per_launch": k1_avg_ms, "share_of_step": k1_avg_ms / (ms_total / args.steps),
+                "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B,
+                "fp32": {"achieved": fp32_achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": fp32_achieved / FP32_PEAK_TFLOPS,
+                         "note": "binding roof: 68 MFLOP/clip of FP32 FFT work vs 0.9 MB of traffic (SURVEY 8d)"}}
+
+    # ---- e2e: host buffers through the public host API, copies inside the timed region --------------------------
+    e2e = None
+    if not args.no_e2e:
+        chunk = min(args.chunk, B)
+        pipe = rt.HostPipe(plan, max_B=B, chunk=chunk)
+        h_in = torch.empty((B, CLIP), dtype=torch.float32, pin_memory=True)
+        h_in.copy_(x)
+        h_out = torch.empty((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, pin_memory=True)
+        pipe.run(h_in, h_out, params)
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            pipe.run(h_in, h_out, params)
+        dt = (time.perf_counter() - t0) / n_e2e
+        dt = dist_.max_over_ranks(dt, device)
+        e2e = {"value": world * B / dt, "unit": "clips/s", "h2d_bytes_per_step": B * CLIP * 4,
+               "d2h_bytes_per_step": B * plan.n_frames * cfg.n_mels * 4, "steps": n_e2e,
+               "api": "HostPipe.run (cacfe_hostpipe_run): pinned host -> H2D -> normalise/STFT/mel/PCEN -> D2H",
+               "checksum": float(h_out[0, :4, :4].sum())}
+        del pipe, h_in, h_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, nb = cpu_reference_run(32, budget_s=15.0)
+        cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{nb} batches of 32 synthetic clips (configs[0]); oracle port of the reference's f32 op order, scipy pocketfft all workers"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"fused normalize -> STFT 4096/281 pad_end -> |z|^2 -> mel 160 -> PCEN (tensor-global min-max), batch {B} clips x 3 s @ 48 kHz per GPU",
+                           "batch_per_gpu": B, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (B * CLIP * 4 / 1e9),
+                           "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "checksum": float(out[0, :4, :4].sum())}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

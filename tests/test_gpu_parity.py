@@ -1,0 +1,264 @@
+"""GPU (`-m gpu`): the CUDA path, called through the C ABI (ctypes) behind the reference-named API, against the
+oracle and the committed golden vectors.
+
+Tolerance (north star): |ours - truth| <= 1e-4 * |truth| + 1e-5, truth = float64 oracle.  Integer / index work
+(frame counts, shapes, window tables) and the f32 normalisation / EMA are compared bit for bit.
+"""
+import numpy as np
+import pytest
+import torch
+
+import audio_training_b200 as atb
+from audio_training_b200 import _runtime as rt
+from audio_training_b200 import tfdataset as td
+
+pytestmark = pytest.mark.gpu
+
+REL, ABS = 1e-4, 1e-5
+
+
+def check(oracle, got, want, scale=1.0, what=""):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert got.shape == np.asarray(want).shape, (got.shape, np.asarray(want).shape)
+    ok, worst = oracle.within_tolerance(got, want, REL * scale, ABS * scale)
+    assert ok, f"{what}: worst error {worst:.3f} x budget"
+    return worst
+
+
+@pytest.fixture(scope="module")
+def bank(oracle):
+    return oracle.mel_f(48000, 160, 100, 11000, 4096, 1000)
+
+
+@pytest.fixture(scope="module")
+def xn(oracle, clips):
+    return oracle.normalize(clips, np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ a1
+def test_normalize_bit_exact(oracle, golden, clips):
+    got, y = atb.normalize(golden["small"], "label")
+    assert y == "label"
+    assert np.array_equal(got, golden["norm_np"])
+    got = atb.normalize_data(torch.from_numpy(clips).cuda())
+    assert got.is_cuda
+    assert np.array_equal(got.cpu().numpy(), oracle.normalize(clips, np.float32))
+    assert np.isnan(atb.normalize_data(np.full((2, 64), 0.25, np.float32))).all()      # Q1: constant clip -> NaN
+    (out, a, b), _ = atb.normalize((golden["small"], "short_f", "mid_f"), None)           # tuple pass-through
+    assert (a, b) == ("short_f", "mid_f") and np.array_equal(out, golden["norm_np"])
+    ragged = np.random.default_rng(0).standard_normal((5, 1001)).astype(np.float32)       # odd length: scalar path
+    assert np.array_equal(atb.normalize_data(ragged), oracle.normalize(ragged, np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ path A
+def test_path_a_vs_golden_and_oracle(oracle, golden, xn, bank):
+    out, _ = atb.raw_to_mel(xn, None)
+    assert out.shape == (2, 160, 513, 3) and out.dtype == np.float32
+    truth = oracle.raw_to_mel(xn, bank, channels=0, dtype=np.float64)
+    for c in range(3):
+        check(oracle, out[..., c], truth, what="path A vs f64 oracle")
+    check(oracle, out[..., 0], golden["path_a"], 2.0, what="path A vs reference-code golden (both f32)")
+    assert np.array_equal(out[..., 0], out[..., 1]) and np.array_equal(out[..., 0], out[..., 2])
+    single, _ = atb.raw_to_mel(xn[1], None)
+    assert single.shape == (160, 513, 3) and np.array_equal(single, out[1])
+
+
+def test_fused_normalize_and_layouts(oracle, clips, xn, bank):
+    t = torch.from_numpy(clips).cuda()
+    truth = oracle.raw_to_mel(xn, bank, channels=0, dtype=np.float64)
+    cfg = rt.FrontendConfig(normalize=True, channels=1)
+    img = rt.get_plan(cfg, 0, bank).frontend(t)
+    assert tuple(img.shape) == (2, 160, 513, 1)
+    check(oracle, img[..., 0], truth, what="fused normalise, BMTC")
+    btm = rt.get_plan(cfg.with_(out_layout="btm"), 0, bank).frontend(t)
+    assert tuple(btm.shape) == (2, 513, 160)
+    assert torch.equal(btm.transpose(1, 2), img[..., 0])
+
+
+def test_analytic_signals(oracle, bank):
+    n = 144000
+    x = np.zeros((3, n), np.float32)
+    x[0, 100000] = 1.0                                             # impulse: exact frame indexing
+    x[1] = np.sin(2 * np.pi * 300 * np.arange(n) / 4096.0)         # bin-centre sine
+    x[2] = 0.25                                                    # DC (normalise off)
+    out, _ = atb.raw_to_mel(x, None)
+    truth = oracle.raw_to_mel(x, bank, channels=0, dtype=np.float64)
+    check(oracle, out[..., 0], truth, what="analytic")
+    frames_hit = np.nonzero(out[0, :, :, 0].sum(axis=0) > 1e-12)[0]
+    want = [t for t in range(513) if 0 <= 100000 - 281 * t < 4096 and oracle.hann_periodic(4096)[100000 - 281 * t] > 1e-4]
+    assert frames_hit.min() <= want[0] and frames_hit.max() >= want[-1]
+    assert out[0, :, :340, 0].max() == 0.0 and out[0, :, 357:, 0].max() == 0.0   # frames that do not cover the impulse
+
+
+def test_other_filterbank(oracle, xn):
+    try:
+        w = td.configure(fmin=500, fmax=11000)                      # tfdataset.py:47 import-time bank
+        out, _ = atb.raw_to_mel(xn[:1], None)
+        check(oracle, out[..., 0], oracle.raw_to_mel(xn[:1], w, channels=0), what="fmin=500 bank")
+        w = td.configure(fmin=50, fmax=23000)                        # reaches past bin 959: the NQ=33 kernel
+        out, _ = atb.raw_to_mel(xn[:1], None)
+        check(oracle, out[..., 0], oracle.raw_to_mel(xn[:1], w, channels=0), what="wide bank")
+    finally:
+        td.configure(fmin=100, fmax=11000)
+
+
+def test_short_and_ragged_clips(oracle):
+    rng = np.random.default_rng(5)
+    for n in (1, 130, 4096, 5000, 281 * 16 + 7):
+        x = rng.uniform(-1, 1, (3, n)).astype(np.float32)
+        w = oracle.mel_f(48000, 160, 100, 11000, 4096, 1000)
+        out, _ = atb.raw_to_mel(x, None)
+        T = -(-n // 281)
+        assert out.shape == (3, 160, T, 3)
+        check(oracle, out[..., 0], oracle.raw_to_mel(x, w, channels=0), what=f"n={n}")
+
+
+def test_batch_invariance(oracle):
+    """Sharding invariance: a clip's features do not depend on its batch mates or its position in the batch."""
+    x = torch.from_numpy(oracle.synth_clips(np.arange(8, 8 + 37))).cuda()
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1), 0)
+    full = plan.frontend(x)
+    part = plan.frontend(x[5:9].contiguous())
+    assert torch.equal(full[5:9], part)
+    assert torch.isfinite(full).all()
+
+
+# ------------------------------------------------------------------------------------------------ path B
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_path_b(oracle, golden, xn, pad_mode):
+    for i in range(2):
+        got = atb.get_spect(xn[i], 48000, 281, False, False, 1000, True, 160, 100, 11000, 4096, 2, False, pad_mode=pad_mode)
+        assert got.shape == (160, 513, 1)
+        check(oracle, got, oracle.get_spect(xn[i], pad_mode=pad_mode), what="path B vs f64 oracle")
+        if pad_mode == "constant":
+            check(oracle, got[..., 0], golden["path_b"][i], 2.0, what="path B vs reference-code golden")
+    got3 = atb.get_spect(xn[0], 48000, 281, False, False, 1000, True, 160, 100, 11000, 4096, 2, False, channels=3)
+    assert got3.shape == (160, 513, 3)
+    db = atb.get_spect(xn[0], 48000, 281, False, False, 1000, True, 160, 100, 11000, 4096, 2, True)
+    check(oracle, db, oracle.get_spect(xn[0], db_scale=True), 5.0, what="db_scale")
+
+
+def test_load_samples(oracle):
+    rng = np.random.default_rng(11)
+    sr = 48000
+    rec = (rng.standard_normal(int(7.5 * sr)) * 0.1).astype(np.float32)
+    tracks = [oracle.Track(0.0, 7.5), oracle.Track(5.0, 7.5), oracle.Track(6.9, 7.4), oracle.Track(1.0, 2.0, 12000, 14000)]
+    got = atb.load_samples(rec, sr, tracks, randint=lambda lo, hi: 0)
+    want = oracle.load_samples(rec, sr, tracks, dtype=np.float64)
+    assert [len(g) for g in got] == [len(w) for w in want] == [5, 1, 1, 0]
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert a.shape == (160, 513, 1)
+            check(oracle, a, b, what="load_samples")
+    short = atb.load_samples(rec[: sr * 2], sr, [oracle.Track(0.0, 2.0)], randint=lambda lo, hi: 1234)
+    want = oracle.load_samples(rec[: sr * 2], sr, [oracle.Track(0.0, 2.0)], rand_offset=lambda e: 1234)
+    check(oracle, short[0][0], want[0][0], what="short recording, padded window")
+
+
+# ------------------------------------------------------------------------------------------------ path C
+def test_path_c(oracle, golden, xn, bank):
+    mag = np.abs(oracle.stft_librosa(xn[0], dtype=np.float32)).astype(np.float32)
+    got = td.mel_from_spectrogram(mag.reshape(-1))
+    assert got.shape == (160, 513, 1)
+    check(oracle, got, oracle.mel_from_spectrogram(mag, bank), what="path C vs f64 oracle")
+    check(oracle, got[..., 0], golden["path_c"], 2.0, what="path C vs reference-code golden")
+    both = td.mel_from_spectrogram(np.stack([mag, mag * 0.5]), model_name="efficientnetb0")
+    assert both.shape == (2, 160, 513, 3)
+    check(oracle, both[1, ..., 2], 0.5 * oracle.mel_from_spectrogram(mag, bank)[..., 0], what="path C batch")
+    spec = atb.mel_spec(mag, 48000, 4096, 281, 160, 100, 11000, 1000, power=2)
+    check(oracle, spec, oracle.mel_spec(mag, 48000, 4096, 281, 160, 100, 11000, 1000, 2), what="mel_spec power 2")
+    small = atb.mel_spec(mag[:1025], 48000, 2048, 278, 96, 100, 11000, 1000, power=1)   # other n_fft: spectrogram path only
+    check(oracle, small, oracle.mel_spec(mag[:1025], 48000, 2048, 278, 96, 100, 11000, 1000, 1), what="mel_spec 2048")
+
+
+# ------------------------------------------------------------------------------------------------ PCEN
+def test_ema_bit_exact(oracle, golden):
+    x = np.swapaxes(golden["path_a"], 1, 2).copy()
+    ema = atb.ExponentialMovingAverage(0.04)
+    got = ema(x, initial_state=x[:, 0, :])
+    assert np.array_equal(got, golden["ema"])
+    assert np.array_equal(got, oracle.ema(x, dtype=np.float32))
+
+
+def test_pcen(oracle, golden):
+    x = np.swapaxes(golden["path_a"], 1, 2).copy()
+    layer = atb.PCEN()
+    got = layer(x)
+    check(oracle, got, oracle.pcen(x), what="PCEN vs f64 oracle")
+    check(oracle, got, golden["pcen"], 2.0, what="PCEN vs reference-code golden")
+    assert got.min() == -1.0 and got.max() == 1.0                       # tfdataset.py:1442-1472 invariant
+    s = golden["small_btf"]
+    check(oracle, atb.PCEN()(s), golden["pcen_small"], 2.0, what="small")
+    l2 = atb.PCEN()
+    l2.load_state_dict({"gain": 1.3, "bias": 1.5, "root": 0.5, "EMA/smooth": 0.25})   # clamps: gain<=1, root>=1
+    check(oracle, l2(s), golden["pcen_small2"], 2.0, what="clamped weights")
+    l3 = atb.PCEN()
+    l3.root[:] = 3.0                                                   # general root: exp2/log2 path
+    check(oracle, l3(s), oracle.pcen(s, root=3.0), what="root 3")
+    per_clip = atb.PCEN(norm_scope="clip")(x)
+    want = np.stack([oracle.pcen(x[i:i + 1])[0] for i in range(2)])
+    check(oracle, per_clip, want, what="clip scope")
+    raw = atb.PCEN(norm_scope="none")(x)
+    check(oracle, raw, oracle.pcen_raw(x), what="no min-max")
+
+
+def test_pcen_image_extension(oracle, golden):
+    img = np.repeat(golden["path_a"][..., None], 3, axis=3)             # [B, 160, 513, 3] as audiomodel.py:793 feeds it
+    got = atb.PCEN()(img)
+    want = oracle.pcen(img, axis=2)
+    check(oracle, got, want, what="rank-4 PCEN")
+
+
+def test_frontend_pcen_fused_call(oracle, clips, bank):
+    t = torch.from_numpy(clips).cuda()
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0, bank)
+    a = plan.frontend_pcen(t)
+    b = plan.pcen(plan.frontend(t))
+    assert torch.equal(a, b)
+    mel = oracle.raw_to_mel(oracle.normalize(clips, np.float32), bank, channels=0)
+    check(oracle, a, oracle.pcen(np.swapaxes(mel, 1, 2)), what="raw -> PCEN")
+
+
+def test_hostpipe_matches_device_path(oracle, bank):
+    x = oracle.synth_clips(np.arange(100, 111))
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0, bank)
+    dev = plan.frontend_pcen(torch.from_numpy(x).cuda()).cpu()
+    pipe = rt.HostPipe(plan, max_B=16, chunk=4)
+    host = pipe.run(torch.from_numpy(x).pin_memory(), params=rt.pcen_params())
+    assert torch.equal(host, dev)
+    mel = pipe.run(x)
+    assert np.array_equal(mel, plan.frontend(torch.from_numpy(x).cuda()).cpu().numpy())
+    per_clip = pipe.run(x, params=rt.pcen_params(norm_scope="clip"))
+    assert np.array_equal(per_clip, plan.pcen(plan.frontend(torch.from_numpy(x).cuda()), rt.pcen_params(norm_scope="clip")).cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ a12-a14
+def test_compress(oracle, golden):
+    mel = golden["path_a"][0]
+    assert np.array_equal(atb.normalize_minmax(mel), golden["normalize_minmax"])
+    assert np.array_equal(td.normalize_minmax(mel), golden["normalize_minmax"])
+    check(oracle, atb.power_to_db(mel), oracle.power_to_db(mel), what="power_to_db")
+    check(oracle, atb.power_to_db(mel), golden["power_to_db"], 2.0, what="power_to_db golden")
+    check(oracle, atb.normalize_std(mel), oracle.normalize_std(mel), what="normalize_std")
+    check(oracle, atb.MagTransform()(mel), oracle.mag_transform(mel), what="MagTransform")
+    check(oracle, atb.MagTransform()(mel), golden["mag_transform"], 2.0, what="MagTransform golden")
+    big = torch.rand(3_000_001, device="cuda") * 7 - 2
+    out = atb.normalize_minmax(big)
+    assert float(out.min()) == -1.0 and float(out.max()) == 1.0
+
+
+# ------------------------------------------------------------------------------------------------ errors
+def test_errors():
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    with pytest.raises(ValueError):
+        plan.frontend(torch.zeros(2, 1000, device="cuda"))
+    with pytest.raises(TypeError):
+        plan.frontend(torch.zeros(2, 144000, device="cuda", dtype=torch.float64))
+    with pytest.raises(atb.CacfeError):
+        rt.Plan(rt.FrontendConfig(n_fft=2048, n_mels=96), 0).frontend(torch.zeros(1, 144000, device="cuda"))
+    with pytest.raises(atb.CacfeError):
+        rt.Plan(rt.FrontendConfig(power=3), 0)
+    with pytest.raises(NotImplementedError):
+        td.raw_to_mel_dual(None, None)
+    assert plan.bin_range() == (9, 938)
+    assert plan.launch_count() >= 0

@@ -1,0 +1,158 @@
+"""CPU (`-m "not gpu"`): the C-ABI library loads and exports what include/cacfe.h declares, the host-side logic of
+the package (filterbank, frame counts, window arithmetic, sharding) matches the reference-derived goldens, and the
+product path refuses to run without a GPU instead of falling back."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, REPO
+
+import audio_training_b200 as atb
+from audio_training_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(REPO, "include", "cacfe.h")).read()
+    declared = set(re.findall(r"\b(cacfe_[a-z_0-9]+)\s*\(", header))
+    declared -= {"cacfe_status"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libcacfe.so does not export {name}"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.cacfe_version() == 100
+
+
+def test_native_filterbank_matches_reference_goldens(golden_banks):
+    lib = _lib.load()
+    for tag in [k for k in golden_banks.files if not k.endswith("_args")]:
+        sr, n_mels, fmin, fmax, n_fft, brk = golden_banks[tag + "_args"]
+        out = np.zeros((int(n_mels), int(n_fft) // 2 + 1), np.float32)
+        rc = lib.cacfe_mel_filterbank(int(sr), int(n_mels), fmin, fmax, int(n_fft), brk,
+                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert rc == 0
+        want = golden_banks[tag]
+        # libm vs numpy's SIMD log10/pow may differ in the last f64 bit: allow 1 f32 ulp, expect (and here get) 0
+        assert np.max(np.abs(out - want) / np.maximum(np.spacing(want), 1e-30)) <= 1.0, tag
+        assert np.array_equal(atb.mel_f(int(sr), int(n_mels), fmin, fmax, int(n_fft), brk), want), tag
+
+
+@pytest.mark.parametrize("n,fl,hop,mode,T", [(144000, 4096, 281, 0, 513), (144000, 4096, 281, 1, 513),
+                                            (144000, 4096, 281, 3, 498), (144000, 2048, 278, 3, 511),
+                                            (144000, 1024, 280, 3, 511), (144000, 1024, 281, 0, 513),
+                                            (4000, 4096, 281, 3, 0), (1, 4096, 281, 0, 1)])
+def test_num_frames(n, fl, hop, mode, T, oracle):
+    assert _lib.load().cacfe_num_frames(n, fl, hop, mode) == T
+    if mode in (0, 3):
+        assert oracle.num_frames_tf(n, fl, hop, mode == 0) == T
+
+
+def test_window_table_matches_reference(oracle):
+    from audio_training_b200.predict_utils import window_table
+    with open(os.path.join(GOLDEN, "load_samples.json")) as fh:
+        cases = json.load(fh)
+    for case in cases:
+        offs = [v for (_, v) in case["offsets"]]
+        calls = []
+
+        def randint(lo, hi):
+            calls.append(hi)
+            return offs[len(calls) - 1]
+
+        tracks = [oracle.Track(*t) for t in case["tracks"]]
+        table = window_table(int(case["total"] * 48000), 48000, tracks, randint=randint)
+        assert [len(r) for r in table] == case["counts"]
+        assert [list(w) for r in table for w in r] == [list(w) for w in case["windows"]]
+        assert calls == [h for (h, _) in case["offsets"]]
+
+
+def test_layers_keep_reference_weights(golden):
+    layer = atb.PCEN()
+    sd = layer.state_dict()
+    assert list(sd) == ["gain", "bias", "root", "EMA/smooth", "a-power"]
+    names = list(golden["pcen_weight_names"])
+    vals = dict(zip(names, golden["pcen_weight_values"]))
+    for k in names:
+        assert np.float32(vals[k]) == sd[k][0]
+    assert atb.MagTransform().state_dict()["a-power"][0] == -1.0
+    assert abs(atb.MagTransform().exponent() - 0.2689414) < 1e-6
+    assert atb.PCEN.serial_key != atb.MagTransform.serial_key  # Q12 not reproduced on purpose
+
+
+def test_configure_follows_get_dataset_quirks():
+    from audio_training_b200 import tfdataset as td
+    try:
+        w = td.configure(n_mels=160)
+        assert np.array_equal(w, atb.mel_f(48000, 160, 100, 11000, 4096, 1000))
+        w = td.configure(fmin=500, fmax=11000)
+        assert np.array_equal(w, atb.mel_f(48000, 160, 500, 11000, 4096, 1000))
+    finally:
+        td.configure(fmin=100, fmax=11000)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU refusal")
+def test_no_cpu_fallback():
+    x = np.zeros((1, 144000), np.float32)
+    for call in (lambda: atb.raw_to_mel(x, None), lambda: atb.normalize(x, None), lambda: atb.PCEN()(np.zeros((1, 4, 4), np.float32)),
+                 lambda: atb.normalize_minmax(x), lambda: atb.MagTransform()(x),
+                 lambda: atb.get_spect(x[0], 48000, 281, False, False, 1000, True, 160, 100, 11000, 4096, 2, False)):
+        with pytest.raises(atb.CacfeError):
+            call()
+    cfg = _lib.Config(48000, 144000, 4096, 281, 0, 160, 100.0, 11000.0, 1000.0, 2, 3, 0, 0, 0, 0, None)
+    handle = ctypes.c_void_p(0)
+    rc = _lib.load().cacfe_plan_create(ctypes.byref(cfg), 0, ctypes.byref(handle))
+    assert rc == -6 and b"no CPU path" in _lib.load().cacfe_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "audio-training_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("oracle's", "").lower() or f in ("frontend_core.cuh",), f
+
+
+def test_shard_indices_cover_everything():
+    from audio_training_b200.distributed import shard_indices
+    for n, r in [(10, 3), (1000000, 8), (7, 8), (4096, 2)]:
+        for mode in ("strided", "block"):
+            got = torch.cat([shard_indices(n, k, r, mode) for k in range(r)])
+            assert sorted(got.tolist()) == list(range(n))
+
+
+def test_gather_features_gloo_world2(tmp_path):
+    """N>1 host logic on CPU: 2 ranks over gloo gather ragged strided shards onto rank 0."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, {REPO!r})
+from audio_training_b200 import distributed as d
+rank, size, _ = d.init(backend="gloo")
+n = 7
+idx = d.shard_indices(n, rank, size)
+local = (idx.float()[:, None] * 10 + torch.arange(3.)[None]).contiguous()
+out = d.gather_features(local, idx, n, dst=0)
+lo, hi = d.global_extremes(local.min(), local.max())
+assert float(lo) == 0.0 and float(hi) == 62.0
+assert d.max_over_ranks(float(rank)) == 1.0
+if rank == 0:
+    want = torch.arange(n).float()[:, None] * 10 + torch.arange(3.)[None]
+    assert torch.equal(out, want), out
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+""")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "GATHER_OK" in res.stdout
