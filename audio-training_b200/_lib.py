@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcacfe.so")
 SOURCES = ["cacfe.cu"]
-HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_pcen.cuh",
+HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_frontend_stream.cuh", "k_pcen.cuh",
            "k_compress.cuh", "k_melspec.cuh", os.path.join("..", "..", "include", "cacfe.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -61,6 +61,7 @@ PROTOTYPES = {
     "cacfe_compress_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "cacfe_plan_launch_count": (c_longlong, [c_void_p]),
     "cacfe_plan_profile": (c_int, [c_void_p, c_int]),
+    "cacfe_plan_force_generic": (c_int, [c_void_p, c_int]),
     "cacfe_plan_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "cacfe_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]),
     "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -113,6 +113,10 @@ class Plan:
     def launch_count(self):
         return int(self._lib.cacfe_plan_launch_count(self._handle))
 
+    def force_generic(self, enable=True):
+        """Use the generic (non-streaming) fused kernel even where the TMA streaming form applies."""
+        _lib.check(self._lib.cacfe_plan_force_generic(self._handle, 1 if enable else 0))
+
     def profile(self, enable=True):
         _lib.check(self._lib.cacfe_plan_profile(self._handle, 1 if enable else 0))
 

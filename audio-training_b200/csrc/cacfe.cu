@@ -13,6 +13,7 @@
 #include "../../include/cacfe.h"
 #include "k_compress.cuh"
 #include "k_frontend.cuh"
+#include "k_frontend_stream.cuh"
 #include "k_melspec.cuh"
 #include "k_pcen.cuh"
 
@@ -53,6 +54,9 @@ struct cacfe_plan {
   int* d_band_start = nullptr;
   int* d_band_ofs = nullptr;
   cacfe::K1Smem k1;
+  cacfe::SSmem ks;
+  bool stream_ok = false;
+  bool force_generic = false;  // tests: run the non-streaming kernel on configurations that allow both
   bool frontend_ok = false;
   std::atomic<long long> launches{0};
   // optional CUDA-event bracket around every K1 launch (bench.py's live per-kernel timing)
@@ -192,8 +196,14 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
 
   // The fused raw->mel kernel exists for n_fft = 4096 (the reference's only shipped configuration); other sizes
   // get a plan for the spectrogram / PCEN / compression entry points and cacfe_frontend refuses them.
-  p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz);
+  p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
+  if (p->k1.total > (size_t)prop.sharedMemPerBlockOptin) p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 0);
   p->frontend_ok = cfg->n_fft == cacfe::kFft && p->k1.total <= (size_t)prop.sharedMemPerBlockOptin;
+  // streaming (TMA) form: needs 16-byte aligned clips and no reflected samples
+  p->ks = cacfe::stream_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
+  if (p->ks.total > (size_t)prop.sharedMemPerBlockOptin) p->ks = cacfe::stream_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 0);
+  p->stream_ok = p->frontend_ok && p->ks.total <= (size_t)prop.sharedMemPerBlockOptin && cfg->n_samples % 4 == 0 &&
+                 cfg->framing != CACFE_FRAME_CENTER_REFLECT;
 
   // tables
   std::vector<float2> tw(4096);
@@ -220,6 +230,10 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
   if (e == cudaSuccess && p->frontend_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
+  if (e == cudaSuccess && p->stream_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
+  if (e == cudaSuccess && p->stream_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
   if (e != cudaSuccess) {
     cacfe_plan_destroy(p);
     return fail(CACFE_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -263,6 +277,12 @@ int cacfe_plan_profile_read(cacfe_plan* p, double* k1_ms, long long* k1_launches
   *k1_ms = total;
   *k1_launches = (long long)p->k1_events.size();
   p->k1_events.clear();
+  return CACFE_OK;
+}
+
+int cacfe_plan_force_generic(cacfe_plan* p, int enable) {
+  if (!p) return fail(CACFE_EINVAL, "plan_force_generic: null plan");
+  p->force_generic = enable != 0;
   return CACFE_OK;
 }
 
@@ -315,7 +335,9 @@ int compress_blocks(long long entries, long long per_entry) {
   return (int)want;
 }
 
-size_t frontend_ws_bytes(int B) { return align256((size_t)B * kMaxSplits * sizeof(float2)); }
+size_t frontend_ws_bytes(int B) {
+  return align256((size_t)B * kMaxSplits * sizeof(float2)) + align256((size_t)B * sizeof(float2));
+}
 
 int check_launch(cacfe_plan* p, const char* what, int n_launches = 1) {
   cudaError_t e = cudaGetLastError();
@@ -389,13 +411,15 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
                 p->cfg.n_fft, p->k1.total);
   cacfe::FrontendArgs a;
   int launches = 1;
-  a.partial = nullptr;
-  a.splits = 1;
+  a.norm = nullptr;
   if (p->cfg.normalize) {
-    a.splits = pick_splits(p, B);
-    a.partial = (const float2*)ws;
-    cacfe::row_minmax_kernel<<<dim3(a.splits, B), 256, 0, st>>>(raw, p->cfg.n_samples, a.splits, (float2*)ws);
-    launches = 2;
+    const int splits = pick_splits(p, B);
+    float2* partial = (float2*)ws;
+    float2* norm = (float2*)((char*)ws + align256((size_t)B * kMaxSplits * sizeof(float2)));
+    cacfe::row_minmax_kernel<<<dim3(splits, B), 256, 0, st>>>(raw, p->cfg.n_samples, splits, partial);
+    cacfe::minmax_finalize_kernel<<<B, 32, 0, st>>>(partial, splits, norm);  // -> (max - min, min) per clip
+    a.norm = norm;
+    launches = 3;
   }
   a.in = raw;
   a.out = feat;
@@ -425,10 +449,21 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
-  if (p->nq <= 15)
-    cacfe::stft_mel_kernel<15><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
-  else
-    cacfe::stft_mel_kernel<33><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
+  const bool stream = p->stream_ok && !p->force_generic && (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
+  if (stream) {
+    a.bw_in_smem = p->ks.bw_in_smem;
+    const unsigned ctas = (unsigned)(grid < p->sm_count ? grid : p->sm_count);  // one persistent CTA per SM
+    if (p->nq <= 15)
+      cacfe::stft_mel_stream_kernel<15><<<ctas, cacfe::kSThreads, p->ks.total, st>>>(a, (int)grid);
+    else
+      cacfe::stft_mel_stream_kernel<33><<<ctas, cacfe::kSThreads, p->ks.total, st>>>(a, (int)grid);
+  } else {
+    a.bw_in_smem = p->k1.bw_in_smem;
+    if (p->nq <= 15)
+      cacfe::stft_mel_kernel<15><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
+    else
+      cacfe::stft_mel_kernel<33><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
+  }
   if (p->profile) {
     cudaEventRecord(ev1, st);
     p->k1_events.emplace_back(ev0, ev1);

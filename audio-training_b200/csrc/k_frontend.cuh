@@ -92,13 +92,13 @@ enum : int { LAYOUT_BMTC = 0, LAYOUT_BTM = 1 };
 struct FrontendArgs {
   const float* in;         // [B][n_samples]
   float* out;              // [B][M][T][C] or [B][T][M]
-  const float2* partial;   // [B][splits] min/max partials, or nullptr: no normalisation
+  const float2* norm;      // [B] (max - min, min) per clip, or nullptr: no normalisation
   const float2* tw;        // [64][64]  W4096^(k1*n2)
   const float* win;        // [2049] periodic Hann, first half + centre
   const float* band_w;     // packed non-zero filterbank weights, band after band
   const int* band_start;   // [M]   first bin of band m, relative to bin_lo
   const int* band_ofs;     // [M+1] prefix offsets into band_w
-  int splits;
+  int bw_in_smem;
   int n_samples, hop, n_frames, n_mels, nnz;
   int origin;              // sample index of frame 0, element 0 (0, or -n_fft/2 for centred framing)
   int reflect;             // centred framing with reflect padding
@@ -113,12 +113,14 @@ constexpr int kTileFrames = 16;     // frames per CTA tile (8 frame pairs, 2 per
 constexpr int kK1Threads = kGroups * 64;
 
 struct K1Smem {
-  int tile_len, tile_pad, out_stride;
+  int tile_len, tile_pad, out_stride, bw_in_smem;
   size_t off_win, off_tile, off_exch, off_out, off_bw, off_bstart, off_bofs, total;
 };
 
-__host__ __device__ inline K1Smem k1_smem_layout(int hop, int n_mels, int nnz) {
+// bw_in_smem = 0: the packed band weights stay in global memory (L1/L2) -- for banks too wide for the CTA's budget.
+__host__ __device__ inline K1Smem k1_smem_layout(int hop, int n_mels, int nnz, int bw_in_smem) {
   K1Smem s;
+  s.bw_in_smem = bw_in_smem;
   s.tile_len = kFft + hop * (kTileFrames - 1);
   s.tile_pad = (s.tile_len + 3) & ~3;
   s.out_stride = n_mels | 1;  // odd stride: transposed read-out is bank-conflict free
@@ -127,7 +129,7 @@ __host__ __device__ inline K1Smem k1_smem_layout(int hop, int n_mels, int nnz) {
   s.off_tile = o;  o += sizeof(float) * s.tile_pad;
   s.off_exch = o;  o += sizeof(float2) * kExchFloat2 * kGroups;
   s.off_out = o;   o += sizeof(float) * ((kTileFrames * s.out_stride + 3) & ~3);
-  s.off_bw = o;    o += sizeof(float) * ((nnz + 3) & ~3);
+  s.off_bw = o;    o += bw_in_smem ? sizeof(float) * ((nnz + 3) & ~3) : 0;
   s.off_bstart = o; o += sizeof(int) * ((n_mels + 3) & ~3);
   s.off_bofs = o;  o += sizeof(int) * ((n_mels + 1 + 3) & ~3);
   s.total = o;
@@ -137,14 +139,14 @@ __host__ __device__ inline K1Smem k1_smem_layout(int hop, int n_mels, int nnz) {
 // NQ = number of 64-bin column groups the filterbank reaches: bins j + 64 q, q < NQ.
 template <int NQ>
 __global__ void __launch_bounds__(kK1Threads, 1) stft_mel_kernel(const FrontendArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const K1Smem L = k1_smem_layout(a.hop, a.n_mels, a.nnz);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const K1Smem L = k1_smem_layout(a.hop, a.n_mels, a.nnz, a.bw_in_smem);
   float2* s_tw = reinterpret_cast<float2*>(smem);
   float* s_win = reinterpret_cast<float*>(smem + L.off_win);
   float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
   float2* s_exch = reinterpret_cast<float2*>(smem + L.off_exch);
   float* s_out = reinterpret_cast<float*>(smem + L.off_out);
-  float* s_bw = reinterpret_cast<float*>(smem + L.off_bw);
+  const float* s_bw = a.bw_in_smem ? reinterpret_cast<const float*>(smem + L.off_bw) : a.band_w;
   int* s_bstart = reinterpret_cast<int*>(smem + L.off_bstart);
   int* s_bofs = reinterpret_cast<int*>(smem + L.off_bofs);
 
@@ -159,17 +161,18 @@ __global__ void __launch_bounds__(kK1Threads, 1) stft_mel_kernel(const FrontendA
     float4* dst = reinterpret_cast<float4*>(s_tw);
     for (int i = tid; i < 2048; i += kK1Threads) dst[i] = src[i];
     for (int i = tid; i < 2049; i += kK1Threads) s_win[i] = a.win[i];
-    for (int i = tid; i < a.nnz; i += kK1Threads) s_bw[i] = a.band_w[i];
+    if (a.bw_in_smem)
+      for (int i = tid; i < a.nnz; i += kK1Threads) reinterpret_cast<float*>(smem + L.off_bw)[i] = a.band_w[i];
     for (int i = tid; i < a.n_mels; i += kK1Threads) s_bstart[i] = a.band_start[i];
     for (int i = tid; i <= a.n_mels; i += kK1Threads) s_bofs[i] = a.band_ofs[i];
   }
   // ---- sample tile: normalise on load (one FMA), zero pad after normalising (Q4) -----------------
   {
     float sc = 1.0f, of = 0.0f;
-    if (a.partial != nullptr) {
-      float mn, mx;
-      fold_partials(a.partial, b, a.splits, mn, mx);
-      const double inv = 1.0 / (double)(mx - mn);   // ((x-mn)/range + 1e-6 - 0.5) * 2  ==  x*sc + of
+    if (a.norm != nullptr) {
+      const float2 rm = a.norm[b];
+      const float mn = rm.y;
+      const double inv = 1.0 / (double)rm.x;   // ((x-mn)/range + 1e-6 - 0.5) * 2  ==  x*sc + of
       sc = (float)(2.0 * inv);
       of = (float)((-(double)mn * inv + 0.000001 - 0.5) * 2.0);
     }

@@ -25,7 +25,7 @@ constexpr int kMelSpecThreads = 128;
 
 // grid = (ceil(T / 128), B); dynamic smem = nnz floats + (2 M + 1) ints
 __global__ void __launch_bounds__(kMelSpecThreads) melspec_banded_kernel(const MelSpecArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   float* s_w = reinterpret_cast<float*>(smem);
   int* s_start = reinterpret_cast<int*>(s_w + ((a.nnz + 3) & ~3));
   int* s_ofs = s_start + a.n_mels;

@@ -123,6 +123,46 @@ def test_batch_invariance(oracle):
     assert torch.isfinite(full).all()
 
 
+def test_streaming_and_generic_kernels_agree(oracle, clips, xn, bank):
+    """The TMA streaming kernel (spectrum-side normalisation) and the generic kernel (time-domain normalisation) are
+    two implementations of the same features: both must sit inside the tolerance of the f64 oracle."""
+    t = torch.from_numpy(clips).cuda()
+    truth = oracle.raw_to_mel(xn, bank, channels=0, dtype=np.float64)
+    for norm, src, ref in ((True, t, truth), (False, torch.from_numpy(xn).cuda(), truth)):
+        cfg = rt.FrontendConfig(normalize=norm, channels=1)
+        plan = rt.Plan(cfg, 0, bank)
+        a = plan.frontend(src)
+        plan.force_generic(True)
+        b = plan.frontend(src)
+        check(oracle, a[..., 0], ref, what="streaming kernel")
+        check(oracle, b[..., 0], ref, what="generic kernel")
+        check(oracle, a, b.cpu().numpy(), 2.0, what="streaming vs generic")
+
+
+def test_dc_bins_and_large_offset(oracle):
+    """Bank reaching bins 0/1 (spectrum-side DC correction) and clips whose DC dwarfs the signal."""
+    x = oracle.synth_clips(np.arange(40, 43))
+    x[1] = x[1] * 0.01 + 5.0                                          # DC 500x the signal
+    x[2] = x[2] * 1e-3 - 0.75
+    xn = oracle.normalize(x, np.float32)
+    for fmin in (2.0, 100.0):
+        w = oracle.mel_f(48000, 160, fmin, 11000, 4096, 1000)
+        plan = rt.Plan(rt.FrontendConfig(normalize=True, channels=1, fmin=fmin), 0, w)
+        if fmin == 2.0:
+            assert plan.bin_range()[0] <= 1
+        got = plan.frontend(torch.from_numpy(x).cuda())
+        check(oracle, got[..., 0], oracle.raw_to_mel(xn, w, channels=0), what=f"fmin={fmin}")
+
+
+def test_constant_clip_is_nan_through_fused_path(oracle):
+    x = oracle.synth_clips(np.arange(3))
+    x[1] = 0.125
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1), 0)
+    out = plan.frontend(torch.from_numpy(x).cuda())
+    assert torch.isnan(out[1]).all()                                    # Q1: 0/0 like the reference
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+
+
 # ------------------------------------------------------------------------------------------------ path B
 @pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
 def test_path_b(oracle, golden, xn, pad_mode):
