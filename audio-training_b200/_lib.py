@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcacfe.so")
 SOURCES = ["cacfe.cu"]
-HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_frontend_stream.cuh", "k_pcen.cuh",
+HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_frontend_stream.cuh", "k_frontend_v3.cuh", "k_pcen.cuh",
            "k_compress.cuh", "k_melspec.cuh", os.path.join("..", "..", "include", "cacfe.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

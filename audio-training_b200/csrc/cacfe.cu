@@ -2,10 +2,12 @@
 // Host side: plan (tables, filterbank in band form), argument checks, launches.  No CPU compute path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +16,7 @@
 #include "k_compress.cuh"
 #include "k_frontend.cuh"
 #include "k_frontend_stream.cuh"
+#include "k_frontend_v3.cuh"
 #include "k_melspec.cuh"
 #include "k_pcen.cuh"
 
@@ -55,7 +58,13 @@ struct cacfe_plan {
   int* d_band_ofs = nullptr;
   cacfe::K1Smem k1;
   cacfe::SSmem ks;
+  cacfe::VSmem kv;
+  cacfe::MelJobs jobs;
+  float4* d_mel_w = nullptr;
+  int* d_mel_desc = nullptr;
   bool stream_ok = false;
+  bool v3_ok = false;
+  int variant = 3;  // 3: persistent small-code kernel; 2: previous streaming kernel (CACFE_K1_VARIANT, experiments)
   bool force_generic = false;  // tests: run the non-streaming kernel on configurations that allow both
   bool frontend_ok = false;
   std::atomic<long long> launches{0};
@@ -205,6 +214,21 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   p->stream_ok = p->frontend_ok && p->ks.total <= (size_t)prop.sharedMemPerBlockOptin && cfg->n_samples % 4 == 0 &&
                  cfg->framing != CACFE_FRAME_CENTER_REFLECT;
 
+  p->jobs = cacfe::build_mel_jobs(p->bank.data(), cfg->n_mels, p->n_bins, 32 * (p->nq <= 15 ? 15 : 33));
+  p->kv = cacfe::v3_smem_layout(cfg->hop, p->jobs.total_quads);
+  bool reflect_fits = true;
+  if (cfg->framing == CACFE_FRAME_CENTER_REFLECT)
+    for (int t0 = 0; t0 < p->n_frames; t0 += cacfe::kVTileFrames) {
+      const long long s_lo = (long long)p->origin + (long long)cfg->hop * t0;
+      const int t1 = std::min(p->n_frames, t0 + cacfe::kVTileFrames);
+      const long long p_max = s_lo + (long long)cfg->hop * (t1 - 1 - t0) + cfg->n_fft - 1;  // last sample a frame reads
+      if (p_max >= cfg->n_samples && 2LL * (cfg->n_samples - 1) - p_max < std::max(s_lo, 0LL)) reflect_fits = false;
+      if (s_lo < 0 && -s_lo >= s_lo + p->kv.tile_len) reflect_fits = false;
+    }
+  p->v3_ok = p->frontend_ok && p->jobs.ok && p->kv.total <= (size_t)prop.sharedMemPerBlockOptin &&
+             cfg->n_samples % 4 == 0 && reflect_fits;
+  if (const char* v = std::getenv("CACFE_K1_VARIANT")) p->variant = std::atoi(v);
+
   // tables
   std::vector<float2> tw(4096);
   for (int k1 = 0; k1 < 64; ++k1)
@@ -234,6 +258,12 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
   if (e == cudaSuccess && p->stream_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
+  if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
+  if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
+  if (e == cudaSuccess && p->v3_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_v3_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
+  if (e == cudaSuccess && p->v3_ok)
+    e = cudaFuncSetAttribute(cacfe::stft_mel_v3_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
   if (e != cudaSuccess) {
     cacfe_plan_destroy(p);
     return fail(CACFE_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -250,6 +280,8 @@ void cacfe_plan_destroy(cacfe_plan* p) {
   cudaFree(p->d_band_w);
   cudaFree(p->d_band_start);
   cudaFree(p->d_band_ofs);
+  cudaFree(p->d_mel_w);
+  cudaFree(p->d_mel_desc);
   delete p;
 }
 
@@ -449,8 +481,25 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
-  const bool stream = p->stream_ok && !p->force_generic && (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
-  if (stream) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
+  const bool v3 = p->v3_ok && !p->force_generic && aligned && p->variant == 3;
+  const bool stream = p->stream_ok && !p->force_generic && aligned;
+  if (v3) {
+    cacfe::MelArgs mj;
+    mj.w = p->d_mel_w;
+    mj.desc = p->d_mel_desc;
+    for (int sgm = 0; sgm < cacfe::kMelMaxSeg; ++sgm) mj.nq[sgm] = p->jobs.nq[sgm];
+    mj.split_seg = p->jobs.split_seg;
+    mj.total_quads = p->jobs.total_quads;
+    a.bw_in_smem = 0;
+    a.tiles_per_clip = (p->n_frames + cacfe::kVTileFrames - 1) / cacfe::kVTileFrames;
+    const long long tiles = (long long)B * a.tiles_per_clip;
+    const unsigned ctas = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);  // one persistent CTA per SM
+    if (p->nq <= 15)
+      cacfe::stft_mel_v3_kernel<15><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    else
+      cacfe::stft_mel_v3_kernel<33><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+  } else if (stream) {
     a.bw_in_smem = p->ks.bw_in_smem;
     const unsigned ctas = (unsigned)(grid < p->sm_count ? grid : p->sm_count);  // one persistent CTA per SM
     if (p->nq <= 15)

@@ -1,0 +1,314 @@
+// K1 (persistent form, round-1 third generation): fused normalise / frame / Hann / rFFT / power / mel for sm_100a.
+//
+// Same arithmetic as stft_mel_kernel (k_frontend.cuh).  What changed, and the ncu evidence for it
+// (profiles/r01_k1_v2_*: stft_mel_stream_kernel, 3.70 ms for 1024 clips, IPC 2.03):
+//   * the largest stall was `no_instruction` (1.76 of 5.92 warp-cycles per issue): that kernel is ~6 300 SASS
+//     instructions (100 KB) of straight-line code with 12 warps at 6 unrelated positions -- it does not fit any
+//     level of the instruction cache.  Here the two 64-point FFT passes of a frame pair run through ONE copy of the
+//     unrolled cacfe_fft64 (a two-trip loop around it), there is one stage-1 load path instead of two, and the mel
+//     loop is rolled: the hot loop is ~40 % of the old size;
+//   * the per-clip normalisation is applied once per staged sample, in place in shared memory (x - min is exact
+//     for clips whose DC dwarfs their range, which the spectrum-side trick of the previous kernel was not), and the
+//     same pass writes the zero padding (Q4: padding happens after normalisation) or the reflected samples, so every
+//     frame -- partial or not -- takes the same code path: 2 LDS + 1 LDS (window) + 2 FMUL per complex point;
+//   * a tile is 12 frames = 6 frame pairs = one pair per 64-thread FFT group per trip, the CTA meets at two
+//     barriers per tile (buffer hand-over), so all 12 warps stay within one trip of each other and share
+//     instruction-cache lines;
+//   * the mel projection is balanced across the 64 threads of a group (serpentine band order, the short last
+//     round split across lane pairs) -- the old order left one warp with 48 taps and the other with 22.
+// Sample tiles still arrive by TMA bulk copy (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a 2-deep ring.
+#pragma once
+#include "cacfe_common.cuh"
+#include "frontend_core.cuh"
+#include "k_frontend.cuh"
+#include "k_frontend_stream.cuh"  // mbarrier / bulk-copy wrappers
+#include "mel_jobs.h"
+
+namespace cacfe {
+
+constexpr int kVGroups = 6;
+constexpr int kVThreads = kVGroups * 64;
+constexpr int kVTileFrames = 2 * kVGroups;
+
+struct VSmem {
+  int tile_len, tile_pad, mel_quads;
+  size_t off_win, off_tile, off_exch, off_melw, off_desc, off_sync, total;
+};
+
+__host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
+  VSmem s;
+  s.mel_quads = mel_quads;
+  s.tile_len = kFft + hop * (kVTileFrames - 1);
+  s.tile_pad = (s.tile_len + 3 + 4) & ~3;          // room for the copy length rounded up to 16 B
+  size_t o = sizeof(float2) * 4096;
+  s.off_win = o;    o += sizeof(float) * 2052;
+  s.off_tile = o;   o += sizeof(float) * s.tile_pad * 2;
+  s.off_exch = o;   o += sizeof(float) * kHalfFloats * kVGroups;
+  s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads > 0 ? mel_quads : 1);
+  s.off_desc = o;   o += sizeof(int) * 64 * kMelMaxSeg;
+  s.off_sync = o;   o += 16;                         // full[2] mbarriers
+  s.total = o;
+  return s;
+}
+
+// Mel job tables of the plan (mel_jobs.h), device copies.
+struct MelArgs {
+  const float4* w;    // [total_quads][64]
+  const int* desc;    // [kMelMaxSeg][64]
+  int nq[kMelMaxSeg];
+  int split_seg, total_quads;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const FrontendArgs a, const MelArgs mj,
+                                                                      const int total_tiles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
+  float2* s_tw = reinterpret_cast<float2*>(smem);
+  float* s_win = reinterpret_cast<float*>(smem + L.off_win);
+  float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
+  float* s_exch = reinterpret_cast<float*>(smem + L.off_exch);
+  float4* s_melw = reinterpret_cast<float4*>(smem + L.off_melw);
+  int* s_desc = reinterpret_cast<int*>(smem + L.off_desc);
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.off_sync);  // [2]
+
+  const int tid = threadIdx.x;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  // Arms buffer i&1 with this CTA's i-th tile: one bulk copy of the samples that lie inside the clip.
+  auto issue_tile = [&](int i) {
+    const int s = i & 1;
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = w / a.tiles_per_clip;
+    const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
+    const int s_lo = a.origin + a.hop * t0;          // multiple of 4: hop * 12 and the origin both are
+    const int c0 = max(s_lo, 0);
+    int c1 = min(s_lo + L.tile_len, a.n_samples);
+    c1 = (c1 + 3) & ~3;                              // n_samples % 4 == 0 on this path, so this never leaves the clip
+    const uint32_t bytes = (uint32_t)(c1 - c0) * 4u;
+    const uint32_t bar = smem_u32(&s_full[s]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses vs the async write
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(s_tile + (size_t)s * L.tile_pad + (c0 - s_lo)), a.in + (size_t)b * a.n_samples + c0, bytes, bar);
+  };
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_full[0]), 1);
+    mbar_init(smem_u32(&s_full[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- tables, once per CTA (L2 resident) ------------------------------------------------------------------
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.tw);
+    float4* dst = reinterpret_cast<float4*>(s_tw);
+    for (int i = tid; i < 2048; i += kVThreads) dst[i] = src[i];
+    for (int i = tid; i < 2049; i += kVThreads) s_win[i] = a.win[i];
+    for (int i = tid; i < 64 * mj.total_quads; i += kVThreads) s_melw[i] = mj.w[i];
+    for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
+  }
+  __syncthreads();
+  if (tid == 0 && my_tiles > 0) issue_tile(0);
+
+  const int g = tid >> 6, t64 = tid & 63, lane = tid & 31;
+  float* ex = s_exch + g * kHalfFloats;
+  float2* pbuf = reinterpret_cast<float2*>(ex);  // (power A, power B) per bin; aliases the exchange tile
+  const int j = stage2_row(t64);
+  const bool self = (j == 0) || (j == 32);
+  const int plane = self ? lane : (lane ^ 16);
+
+  float2 nrm_next = make_float2(2.0f, 0.0f);  // (range, min): identity mapping is range 2, min -1 -- see below
+  if (a.norm != nullptr && my_tiles > 0) nrm_next = a.norm[(int)blockIdx.x / a.tiles_per_clip];
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int s = i & 1;
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = w / a.tiles_per_clip;
+    const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
+    const int s_lo = a.origin + a.hop * t0;
+    const float2 nrm = nrm_next;
+    float* tile = s_tile + (size_t)s * L.tile_pad;
+
+    __syncthreads();  // every group has finished trip i-1: buffer s^1 may be overwritten
+    if (i + 1 < my_tiles) {
+      if (tid == 0) issue_tile(i + 1);
+      if (a.norm != nullptr) nrm_next = a.norm[(w + (int)gridDim.x) / a.tiles_per_clip];
+    }
+    mbar_wait(smem_u32(&s_full[s]), (uint32_t)((i >> 1) & 1));
+
+    // ---- normalise in place, write the padding -------------------------------------------------------------------
+    {
+      float mn = 0.0f, sc = 1.0f, of = 0.0f;
+      if (a.norm != nullptr) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
+        mn = nrm.y;
+        sc = 2.0f / nrm.x;      // range 0 -> inf -> (x - mn) * inf = NaN: constant clips give NaN features (Q1)
+        of = -0.999998f;
+      }
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      const int n4 = L.tile_pad >> 2;
+      for (int e = tid; e < n4; e += kVThreads) {
+        const int p = s_lo + 4 * e;
+        float4 v = t4[e];
+        if (p >= 0 && p + 3 < a.n_samples) {
+          v.x = fmaf(v.x - mn, sc, of);
+          v.y = fmaf(v.y - mn, sc, of);
+          v.z = fmaf(v.z - mn, sc, of);
+          v.w = fmaf(v.w - mn, sc, of);
+        } else {
+          v.x = (p >= 0 && p < a.n_samples) ? fmaf(v.x - mn, sc, of) : 0.0f;
+          v.y = (p + 1 >= 0 && p + 1 < a.n_samples) ? fmaf(v.y - mn, sc, of) : 0.0f;
+          v.z = (p + 2 >= 0 && p + 2 < a.n_samples) ? fmaf(v.z - mn, sc, of) : 0.0f;
+          v.w = (p + 3 >= 0 && p + 3 < a.n_samples) ? fmaf(v.w - mn, sc, of) : 0.0f;
+        }
+        t4[e] = v;
+      }
+      if (a.reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
+        __syncthreads();
+        for (int e = tid; e < L.tile_len; e += kVThreads) {
+          const int p = s_lo + e;
+          int r = p;
+          if (p < 0) r = -p;
+          if (p >= a.n_samples) r = 2 * (a.n_samples - 1) - p;
+          if (r != p && r >= s_lo && r >= 0 && r < a.n_samples) tile[e] = tile[r - s_lo];  // host checked: always true for samples a frame reads
+        }
+      }
+    }
+    __syncthreads();
+
+    const int ta = t0 + 2 * g;
+    if (ta >= a.n_frames) continue;  // group-uniform; the CTA barriers are at the top of the loop
+    const bool store_b = ta + 1 < a.n_frames;
+
+    float re[64], im[64];
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+      if (ph == 0) {
+        // ---- stage 1 input: window; z[n] = w[n] (xA[n] + i xB[n]), thread n2 = t64 holds n = 64 q + n2 ----------------
+        const float* fa = tile + (2 * g) * a.hop;
+        const float* fb = fa + a.hop;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) {
+          const int n = 64 * q + t64;
+          const float wv = s_win[q < 32 ? n : kFft - n];
+          re[q] = fa[n] * wv;
+          im[q] = fb[n] * wv;
+        }
+      }
+      cacfe_fft64(re, im);
+      if (ph == 0) {
+        // ---- twiddle W4096^(n2 k1), then the transpose through shared memory, real parts first ------------------------
+#pragma unroll
+        for (int k1 = 1; k1 < 64; ++k1) {
+          const int sl = CACFE_FFT64_SLOT(k1);
+          const float2 t = s_tw[k1 * 64 + t64];
+          const float yr = re[sl] * t.x - im[sl] * t.y;
+          const float yi = re[sl] * t.y + im[sl] * t.x;
+          re[sl] = yr;
+          im[sl] = yi;
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = re[CACFE_FFT64_SLOT(k1)];
+        group_barrier(1 + g, 64);
+        {
+          const float4* row = reinterpret_cast<const float4*>(ex + j * kHalfStride);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 v = row[q];
+            re[4 * q] = v.x;
+            re[4 * q + 1] = v.y;
+            re[4 * q + 2] = v.z;
+            re[4 * q + 3] = v.w;
+          }
+        }
+        group_barrier(1 + g, 64);
+        // re[] now holds stage-2 inputs in natural order while im[] still holds stage-1 outputs in slot order
+#pragma unroll
+        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = im[CACFE_FFT64_SLOT(k1)];
+        group_barrier(1 + g, 64);
+        {
+          const float4* row = reinterpret_cast<const float4*>(ex + j * kHalfStride);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 v = row[q];
+            im[4 * q] = v.x;
+            im[4 * q + 1] = v.y;
+            im[4 * q + 2] = v.z;
+            im[4 * q + 3] = v.w;
+          }
+        }
+        group_barrier(1 + g, 64);  // the exchange tile may now be overwritten with powers
+      }
+    }
+
+    // ---- split the two frames, power: bin k = j + 64 q goes to pbuf[k] --------------------------------------------------
+    const bool row0 = j == 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      // Z[N-k]: thread 64-j holds it in slot 63-q; row 0 pairs with its own slot (64-q)&63
+      const float sr = __shfl_sync(kFullMask, re[CACFE_FFT64_SLOT(63 - q)], plane);
+      const float si = __shfl_sync(kFullMask, im[CACFE_FFT64_SLOT(63 - q)], plane);
+      const float pr = row0 ? re[CACFE_FFT64_SLOT((64 - q) & 63)] : sr;
+      const float pi = row0 ? im[CACFE_FFT64_SLOT((64 - q) & 63)] : si;
+      const float zr = re[CACFE_FFT64_SLOT(q)], zi = im[CACFE_FFT64_SLOT(q)];
+      const float ar = zr + pr, ai = zi - pi;   // 2 XA
+      const float br = zr - pr, bi = zi + pi;   // 2i XB
+      const int k = j + 64 * q;  // bin -> 16-byte chunk k >> 1, swizzled (mel_jobs.h)
+      pbuf[2 * mel_swizzle(k >> 1) + (k & 1)] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+    }
+    group_barrier(1 + g, 64);
+    if (a.power == 1) {  // magnitude (stored-spectrogram convention, tfdataset.py:1085-1088): rolled, off the hot path
+      for (int k = t64; k < 64 * NQ; k += 64) {  // element-wise: the swizzle does not matter
+        const float2 v = pbuf[k];
+        pbuf[k] = make_float2(sqrtf(v.x), sqrtf(v.y));
+      }
+      group_barrier(1 + g, 64);
+    }
+
+    // ---- banded mel projection (mel_jobs.h), both frames of the pair per thread, straight to global -------------------
+    {
+      const size_t row = (size_t)b * a.n_frames + ta;
+      const long long m_stride = a.layout == LAYOUT_BTM ? 1 : (long long)a.n_frames * a.channels;
+      const int f_stride = a.layout == LAYOUT_BTM ? a.n_mels : a.channels;
+      float* obase = a.layout == LAYOUT_BTM ? a.out + row * a.n_mels
+                                            : a.out + ((size_t)b * a.n_mels * a.n_frames + ta) * a.channels;
+      const float4* p4 = reinterpret_cast<const float4*>(pbuf);
+      const float4* wq = s_melw + t64;
+#pragma unroll
+      for (int sg = 0; sg < kMelMaxSeg; ++sg) {
+        const int nq = mj.nq[sg];
+        if (nq == 0) continue;  // uniform
+        const int d = s_desc[sg * 64 + t64];
+        int c = (d >> 8) & 0xffff;
+        float acc_a = 0.0f, acc_b = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i < nq; ++i, c += 2, wq += 64) {
+          const float4 wv = *wq;
+          const float4 p01 = p4[mel_swizzle(c)];      // (A[k], B[k], A[k+1], B[k+1])
+          const float4 p23 = p4[mel_swizzle(c + 1)];
+          acc_a = fmaf(wv.x, p01.x, acc_a);
+          acc_b = fmaf(wv.x, p01.y, acc_b);
+          acc_a = fmaf(wv.y, p01.z, acc_a);
+          acc_b = fmaf(wv.y, p01.w, acc_b);
+          acc_a = fmaf(wv.z, p23.x, acc_a);
+          acc_b = fmaf(wv.z, p23.y, acc_b);
+          acc_a = fmaf(wv.w, p23.z, acc_a);
+          acc_b = fmaf(wv.w, p23.w, acc_b);
+        }
+        if (sg == mj.split_seg) {  // uniform: lanes 2i / 2i+1 hold the two halves of one band
+          acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
+          acc_b += __shfl_xor_sync(kFullMask, acc_b, 1);
+        }
+        if ((d >> 25) & 1) {
+          float* o = obase + (d & 0xff) * m_stride;
+#pragma unroll 1
+          for (int ch = 0; ch < a.channels; ++ch) {
+            o[ch] = acc_a;
+            if (store_b) o[f_stride + ch] = acc_b;
+          }
+        }
+      }
+    }
+    // (the next trip's exchange writes come after two CTA barriers: no group barrier needed here)
+  }
+}
+
+}  // namespace cacfe

@@ -45,3 +45,68 @@ extern "C" int k1_emul_pair(const float* fa, const float* fb, int power, float* 
   }
   return 0;
 }
+
+// ---- mel job tables (mel_jobs.h): run the kernel's quad loop on the host ------------------------------------------
+#include "mel_jobs.h"
+
+// power: [2 * n_chunks] bins of one frame (frame B of the pair is set to 2x frame A); out: [n_mels] for frame A and
+// [n_mels] for frame B.  Returns 0, or a positive code when the tables are inconsistent.
+extern "C" int mel_jobs_emul(const float* bank, int n_mels, int n_bins, int n_chunks, const float* power, float* out_a,
+                             float* out_b, int* total_quads) {
+  const MelJobs J = build_mel_jobs(bank, n_mels, n_bins, n_chunks);
+  if (!J.ok) return 1;
+  *total_quads = J.total_quads;
+  // the kernel's power buffer: float2 (A, B) per bin, 16-byte chunks swizzled
+  std::vector<float> pbuf((size_t)4 * n_chunks, 0.0f);
+  for (int k = 0; k < 2 * n_chunks; ++k) {
+    const int idx = 2 * mel_swizzle(k >> 1) + (k & 1);
+    if (idx < 0 || idx >= 2 * n_chunks) return 2;
+    pbuf[2 * idx] = power[k];
+    pbuf[2 * idx + 1] = 2.0f * power[k];
+  }
+  std::vector<int> written(n_mels, 0);
+  int qbase = 0;
+  for (int sg = 0; sg < kMelMaxSeg; ++sg) {
+    const int nq = J.nq[sg];
+    if (nq == 0) continue;
+    float acc_a[64], acc_b[64];
+    for (int t = 0; t < 64; ++t) {
+      const int d = J.desc[sg * 64 + t];
+      int c = mel_desc_chunk(d);
+      acc_a[t] = acc_b[t] = 0.0f;
+      for (int i = 0; i < nq; ++i, c += 2) {
+        if (c < 0 || c + 1 >= n_chunks) return 3;
+        const float* wv = &J.w[(((size_t)(qbase + i)) * 64 + t) * 4];
+        const float* p01 = &pbuf[4 * mel_swizzle(c)];
+        const float* p23 = &pbuf[4 * mel_swizzle(c + 1)];
+        acc_a[t] = std::fmaf(wv[0], p01[0], acc_a[t]);
+        acc_b[t] = std::fmaf(wv[0], p01[1], acc_b[t]);
+        acc_a[t] = std::fmaf(wv[1], p01[2], acc_a[t]);
+        acc_b[t] = std::fmaf(wv[1], p01[3], acc_b[t]);
+        acc_a[t] = std::fmaf(wv[2], p23[0], acc_a[t]);
+        acc_b[t] = std::fmaf(wv[2], p23[1], acc_b[t]);
+        acc_a[t] = std::fmaf(wv[3], p23[2], acc_a[t]);
+        acc_b[t] = std::fmaf(wv[3], p23[3], acc_b[t]);
+      }
+    }
+    if (sg == J.split_seg)
+      for (int t = 0; t < 64; t += 2) {
+        const float sa = acc_a[t] + acc_a[t + 1], sb = acc_b[t] + acc_b[t + 1];
+        acc_a[t] = acc_a[t + 1] = sa;
+        acc_b[t] = acc_b[t + 1] = sb;
+      }
+    for (int t = 0; t < 64; ++t) {
+      const int d = J.desc[sg * 64 + t];
+      if (!mel_desc_stores(d)) continue;
+      const int m = mel_desc_band(d);
+      if (m >= n_mels) return 4;
+      out_a[m] = acc_a[t];
+      out_b[m] = acc_b[t];
+      written[m]++;
+    }
+    qbase += nq;
+  }
+  for (int m = 0; m < n_mels; ++m)
+    if (written[m] != 1) return 5;  // every band stored exactly once
+  return 0;
+}
