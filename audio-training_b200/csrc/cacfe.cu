@@ -482,7 +482,8 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     cudaEventRecord(ev0, st);
   }
   const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
-  const bool v3 = p->v3_ok && !p->force_generic && aligned && p->variant == 3;
+  const bool v3 = p->v3_ok && !p->force_generic && aligned && p->variant == 3 &&
+                  (reinterpret_cast<uintptr_t>(a.norm) & 15) == 0;  // the kernel bulk-copies 16-byte pairs of it
   const bool stream = p->stream_ok && !p->force_generic && aligned;
   if (v3) {
     cacfe::MelArgs mj;

@@ -46,7 +46,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
   s.off_exch = o;   o += sizeof(float) * kHalfFloats * kVGroups;
   s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads > 0 ? mel_quads : 1);
   s.off_desc = o;   o += sizeof(int) * 64 * kMelMaxSeg;
-  s.off_sync = o;   o += 16;                         // full[2] mbarriers
+  s.off_sync = o;   o += 96;                         // full/norm/pre mbarriers, done counters, normalisation pairs
   s.total = o;
   return s;
 }
@@ -72,10 +72,17 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   int* s_desc = reinterpret_cast<int*>(smem + L.off_desc);
   uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + L.off_sync);  // [2]
 
+  uint64_t* s_norm = s_full + 2;                                      // [2] tile normalised (12 warp arrivals)
+  uint64_t* s_pre = s_full + 4;                                       // [2] reflect framing: first pass done
+  int* s_done = reinterpret_cast<int*>(s_full + 6);                   // [2] groups that have read the tile
+  float2* s_nrm = reinterpret_cast<float2*>(s_full + 8);              // [2][2] (range, min) of clips b & ~1, b | 1
+
   const int tid = threadIdx.x;
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g = tid >> 6, t64 = tid & 63, lane = tid & 31;
 
-  // Arms buffer i&1 with this CTA's i-th tile: one bulk copy of the samples that lie inside the clip.
+  // Arms buffer i&1 with this CTA's i-th tile: one bulk copy of the samples that lie inside the clip, one of the
+  // clip's normalisation pair.
   auto issue_tile = [&](int i) {
     const int s = i & 1;
     const int w = (int)blockIdx.x + i * (int)gridDim.x;
@@ -88,13 +95,84 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const uint32_t bytes = (uint32_t)(c1 - c0) * 4u;
     const uint32_t bar = smem_u32(&s_full[s]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses vs the async write
-    mbar_expect_tx(bar, bytes);
+    mbar_expect_tx(bar, bytes + (a.norm != nullptr ? 16u : 0u));
     bulk_g2s(smem_u32(s_tile + (size_t)s * L.tile_pad + (c0 - s_lo)), a.in + (size_t)b * a.n_samples + c0, bytes, bar);
+    if (a.norm != nullptr) bulk_g2s(smem_u32(s_nrm + 2 * s), a.norm + (b & ~1), 16u, bar);
+  };
+
+  // Every warp normalises its slice of tile i in place (and writes the padding), then arrives on s_norm[i&1].
+  auto normalise_tile = [&](int i) {
+    const int s = i & 1;
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = w / a.tiles_per_clip;
+    const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
+    const int s_lo = a.origin + a.hop * t0;
+    float* tile = s_tile + (size_t)s * L.tile_pad;
+    const uint32_t parity = (uint32_t)((i >> 1) & 1);
+    mbar_wait(smem_u32(&s_full[s]), parity);
+    float mn = 0.0f, sc = 1.0f, of = 0.0f;
+    if (a.norm != nullptr) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
+      const float2 nrm = s_nrm[2 * s + (b & 1)];
+      mn = nrm.y;
+      sc = 2.0f / nrm.x;      // range 0 -> inf -> (x - mn) * inf = NaN: constant clips give NaN features (Q1)
+      of = -0.999998f;
+    }
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    const int n4 = L.tile_pad >> 2;
+    for (int e = tid; e < n4; e += kVThreads) {
+      const int p = s_lo + 4 * e;
+      float4 v = t4[e];
+      if (p >= 0 && p + 3 < a.n_samples) {
+        v.x = fmaf(v.x - mn, sc, of);
+        v.y = fmaf(v.y - mn, sc, of);
+        v.z = fmaf(v.z - mn, sc, of);
+        v.w = fmaf(v.w - mn, sc, of);
+      } else {
+        v.x = (p >= 0 && p < a.n_samples) ? fmaf(v.x - mn, sc, of) : 0.0f;
+        v.y = (p + 1 >= 0 && p + 1 < a.n_samples) ? fmaf(v.y - mn, sc, of) : 0.0f;
+        v.z = (p + 2 >= 0 && p + 2 < a.n_samples) ? fmaf(v.z - mn, sc, of) : 0.0f;
+        v.w = (p + 3 >= 0 && p + 3 < a.n_samples) ? fmaf(v.w - mn, sc, of) : 0.0f;
+      }
+      t4[e] = v;
+    }
+    if (a.reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_pre[s]));
+      mbar_wait(smem_u32(&s_pre[s]), parity);
+      for (int e = tid; e < L.tile_len; e += kVThreads) {
+        const int p = s_lo + e;
+        int r = p;
+        if (p < 0) r = -p;
+        if (p >= a.n_samples) r = 2 * (a.n_samples - 1) - p;
+        if (r != p && r >= s_lo && r >= 0 && r < a.n_samples) tile[e] = tile[r - s_lo];  // host checked: true for samples a frame reads
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&s_norm[s]));
+  };
+
+  // A group has read tile i into registers; the last of the six re-arms the buffer with tile i + 2.
+  auto release_tile = [&](int i) {
+    group_barrier(1 + g, 64);
+    if (t64 == 0) {
+      const int s = i & 1;
+      __threadfence_block();
+      const int old = atomicAdd(&s_done[s], 1);
+      if (old == kVGroups - 1) {
+        __threadfence_block();
+        s_done[s] = 0;
+        if (i + 2 < my_tiles) issue_tile(i + 2);
+      }
+    }
   };
 
   if (tid == 0) {
-    mbar_init(smem_u32(&s_full[0]), 1);
-    mbar_init(smem_u32(&s_full[1]), 1);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(smem_u32(&s_full[q]), 1);
+      mbar_init(smem_u32(&s_norm[q]), kVThreads / 32);
+      mbar_init(smem_u32(&s_pre[q]), kVThreads / 32);
+      s_done[q] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // ---- tables, once per CTA (L2 resident) ------------------------------------------------------------------
@@ -107,75 +185,34 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
   }
   __syncthreads();
-  if (tid == 0 && my_tiles > 0) issue_tile(0);
+  if (tid == 0) {
+    if (my_tiles > 0) issue_tile(0);
+    if (my_tiles > 1) issue_tile(1);
+  }
+  if (my_tiles > 0) normalise_tile(0);
 
-  const int g = tid >> 6, t64 = tid & 63, lane = tid & 31;
   float* ex = s_exch + g * kHalfFloats;
   float2* pbuf = reinterpret_cast<float2*>(ex);  // (power A, power B) per bin; aliases the exchange tile
   const int j = stage2_row(t64);
   const bool self = (j == 0) || (j == 32);
   const int plane = self ? lane : (lane ^ 16);
 
-  float2 nrm_next = make_float2(2.0f, 0.0f);  // (range, min): identity mapping is range 2, min -1 -- see below
-  if (a.norm != nullptr && my_tiles > 0) nrm_next = a.norm[(int)blockIdx.x / a.tiles_per_clip];
-
+  // The six groups run free: there is no CTA-wide barrier in the loop, only the two mbarrier hand-overs per tile.
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i & 1;
     const int w = (int)blockIdx.x + i * (int)gridDim.x;
     const int b = w / a.tiles_per_clip;
     const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
-    const int s_lo = a.origin + a.hop * t0;
-    const float2 nrm = nrm_next;
     float* tile = s_tile + (size_t)s * L.tile_pad;
 
-    __syncthreads();  // every group has finished trip i-1: buffer s^1 may be overwritten
-    if (i + 1 < my_tiles) {
-      if (tid == 0) issue_tile(i + 1);
-      if (a.norm != nullptr) nrm_next = a.norm[(w + (int)gridDim.x) / a.tiles_per_clip];
-    }
-    mbar_wait(smem_u32(&s_full[s]), (uint32_t)((i >> 1) & 1));
-
-    // ---- normalise in place, write the padding -------------------------------------------------------------------
-    {
-      float mn = 0.0f, sc = 1.0f, of = 0.0f;
-      if (a.norm != nullptr) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
-        mn = nrm.y;
-        sc = 2.0f / nrm.x;      // range 0 -> inf -> (x - mn) * inf = NaN: constant clips give NaN features (Q1)
-        of = -0.999998f;
-      }
-      float4* t4 = reinterpret_cast<float4*>(tile);
-      const int n4 = L.tile_pad >> 2;
-      for (int e = tid; e < n4; e += kVThreads) {
-        const int p = s_lo + 4 * e;
-        float4 v = t4[e];
-        if (p >= 0 && p + 3 < a.n_samples) {
-          v.x = fmaf(v.x - mn, sc, of);
-          v.y = fmaf(v.y - mn, sc, of);
-          v.z = fmaf(v.z - mn, sc, of);
-          v.w = fmaf(v.w - mn, sc, of);
-        } else {
-          v.x = (p >= 0 && p < a.n_samples) ? fmaf(v.x - mn, sc, of) : 0.0f;
-          v.y = (p + 1 >= 0 && p + 1 < a.n_samples) ? fmaf(v.y - mn, sc, of) : 0.0f;
-          v.z = (p + 2 >= 0 && p + 2 < a.n_samples) ? fmaf(v.z - mn, sc, of) : 0.0f;
-          v.w = (p + 3 >= 0 && p + 3 < a.n_samples) ? fmaf(v.w - mn, sc, of) : 0.0f;
-        }
-        t4[e] = v;
-      }
-      if (a.reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
-        __syncthreads();
-        for (int e = tid; e < L.tile_len; e += kVThreads) {
-          const int p = s_lo + e;
-          int r = p;
-          if (p < 0) r = -p;
-          if (p >= a.n_samples) r = 2 * (a.n_samples - 1) - p;
-          if (r != p && r >= s_lo && r >= 0 && r < a.n_samples) tile[e] = tile[r - s_lo];  // host checked: always true for samples a frame reads
-        }
-      }
-    }
-    __syncthreads();
+    if (i + 1 < my_tiles) normalise_tile(i + 1);   // buffer s^1: its TMA was issued when tile i-1 had been read by all
+    mbar_wait(smem_u32(&s_norm[s]), (uint32_t)((i >> 1) & 1));
 
     const int ta = t0 + 2 * g;
-    if (ta >= a.n_frames) continue;  // group-uniform; the CTA barriers are at the top of the loop
+    if (ta >= a.n_frames) {  // group-uniform
+      release_tile(i);
+      continue;
+    }
     const bool store_b = ta + 1 < a.n_frames;
 
     float re[64], im[64];
@@ -192,6 +229,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           re[q] = fa[n] * wv;
           im[q] = fb[n] * wv;
         }
+        release_tile(i);
       }
       cacfe_fft64(re, im);
       if (ph == 0) {
@@ -307,7 +345,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         }
       }
     }
-    // (the next trip's exchange writes come after two CTA barriers: no group barrier needed here)
+    // (the next trip's exchange stores come after release_tile's group barrier: the powers have been consumed by then)
   }
 }
 
