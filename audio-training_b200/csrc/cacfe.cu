@@ -61,6 +61,7 @@ struct cacfe_plan {
   cacfe::VSmem kv;
   cacfe::MelJobs jobs;
   float4* d_mel_w = nullptr;
+  float4* d_tw4 = nullptr;
   int* d_mel_desc = nullptr;
   bool stream_ok = false;
   bool v3_ok = false;
@@ -236,6 +237,14 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
       const double ang = -2.0 * M_PI * (double)((k1 * n2) % 4096) / 4096.0;
       tw[k1 * 64 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
+  std::vector<float> tw4(32 * 64 * 4);  // persistent kernel: twiddles of output pair (k, k+1), k even, for thread n2
+  for (int pr = 0; pr < 32; ++pr)
+    for (int n2 = 0; n2 < 64; ++n2)
+      for (int h = 0; h < 2; ++h) {
+        const double ang = -2.0 * M_PI * (double)(((2 * pr + h) * n2) % 4096) / 4096.0;
+        tw4[(pr * 64 + n2) * 4 + h] = (float)std::cos(ang);
+        tw4[(pr * 64 + n2) * 4 + 2 + h] = (float)std::sin(ang);
+      }
   std::vector<float> win(2049);
   for (int n = 0; n <= 2048; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / 4096.0));
 
@@ -259,6 +268,7 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->stream_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
+  if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_v3_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
@@ -281,6 +291,7 @@ void cacfe_plan_destroy(cacfe_plan* p) {
   cudaFree(p->d_band_start);
   cudaFree(p->d_band_ofs);
   cudaFree(p->d_mel_w);
+  cudaFree(p->d_tw4);
   cudaFree(p->d_mel_desc);
   delete p;
 }
@@ -488,6 +499,7 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
   if (v3) {
     cacfe::MelArgs mj;
     mj.w = p->d_mel_w;
+    mj.tw4 = p->d_tw4;
     mj.desc = p->d_mel_desc;
     for (int sgm = 0; sgm < cacfe::kMelMaxSeg; ++sgm) mj.nq[sgm] = p->jobs.nq[sgm];
     mj.split_seg = p->jobs.split_seg;

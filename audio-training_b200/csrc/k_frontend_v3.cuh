@@ -22,6 +22,7 @@
 #include "frontend_core.cuh"
 #include "k_frontend.cuh"
 #include "k_frontend_stream.cuh"  // mbarrier / bulk-copy wrappers
+#include "fft64x2_gen.cuh"
 #include "mel_jobs.h"
 
 namespace cacfe {
@@ -44,7 +45,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
   s.off_win = o;    o += sizeof(float) * 2052;
   s.off_tile = o;   o += sizeof(float) * s.tile_pad * 2;
   s.off_exch = o;   o += sizeof(float) * kHalfFloats * kVGroups;
-  s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads > 0 ? mel_quads : 1);
+  s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads + 1);   // + 1: the mel loop prefetches one quad ahead
   s.off_desc = o;   o += sizeof(int) * 64 * kMelMaxSeg;
   s.off_sync = o;   o += 96;                         // full/norm/pre mbarriers, done counters, normalisation pairs
   s.total = o;
@@ -53,6 +54,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
 
 // Mel job tables of the plan (mel_jobs.h), device copies.
 struct MelArgs {
+  const float4* tw4;  // [32][64] stage twiddles, packed per output pair: (cos k, cos k+1, sin k, sin k+1)
   const float4* w;    // [total_quads][64]
   const int* desc;    // [kMelMaxSeg][64]
   int nq[kMelMaxSeg];
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
                                                                       const int total_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
-  float2* s_tw = reinterpret_cast<float2*>(smem);
+  float4* s_tw4 = reinterpret_cast<float4*>(smem);   // [32 output pairs][64 n2]
   float* s_win = reinterpret_cast<float*>(smem + L.off_win);
   float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
   float* s_exch = reinterpret_cast<float*>(smem + L.off_exch);
@@ -177,11 +179,10 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   }
   // ---- tables, once per CTA (L2 resident) ------------------------------------------------------------------
   {
-    const float4* src = reinterpret_cast<const float4*>(a.tw);
-    float4* dst = reinterpret_cast<float4*>(s_tw);
-    for (int i = tid; i < 2048; i += kVThreads) dst[i] = src[i];
+    for (int i = tid; i < 2048; i += kVThreads) s_tw4[i] = mj.tw4[i];
     for (int i = tid; i < 2049; i += kVThreads) s_win[i] = a.win[i];
-    for (int i = tid; i < 64 * mj.total_quads; i += kVThreads) s_melw[i] = mj.w[i];
+    for (int i = tid; i < 64 * (mj.total_quads + 1); i += kVThreads)
+      s_melw[i] = i < 64 * mj.total_quads ? mj.w[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
   }
   __syncthreads();
@@ -223,28 +224,36 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         const float* fa = tile + (2 * g) * a.hop;
         const float* fb = fa + a.hop;
 #pragma unroll
-        for (int q = 0; q < 64; ++q) {
+        for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
           const int n = 64 * q + t64;
-          const float wv = s_win[q < 32 ? n : kFft - n];
-          re[q] = fa[n] * wv;
-          im[q] = fb[n] * wv;
+          const cacfe_f2 wv = cacfe_pk(s_win[q < 32 ? n : kFft - n], s_win[q + 1 < 32 ? n + 64 : kFft - n - 64]);
+          const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv);
+          const cacfe_f2 xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
+          re[q] = cacfe_lo(xa);
+          re[q + 1] = cacfe_hi(xa);
+          im[q] = cacfe_lo(xb);
+          im[q + 1] = cacfe_hi(xb);
         }
         release_tile(i);
       }
-      cacfe_fft64(re, im);
+      cacfe_fft64x2(re, im);
       if (ph == 0) {
         // ---- twiddle W4096^(n2 k1), then the transpose through shared memory, real parts first ------------------------
 #pragma unroll
-        for (int k1 = 1; k1 < 64; ++k1) {
-          const int sl = CACFE_FFT64_SLOT(k1);
-          const float2 t = s_tw[k1 * 64 + t64];
-          const float yr = re[sl] * t.x - im[sl] * t.y;
-          const float yi = re[sl] * t.y + im[sl] * t.x;
-          re[sl] = yr;
-          im[sl] = yi;
+        for (int k = 0; k < 64; k += 2) {  // outputs k, k + 1 leave cacfe_fft64x2 in one register pair
+          const int s0 = k, s1 = k + 1;
+          const float4 t = s_tw4[(k >> 1) * 64 + t64];  // (cos k, cos k+1, sin k, sin k+1) of -2 pi k n2 / 4096
+          const cacfe_f2 tr = cacfe_pk(t.x, t.y), ti = cacfe_pk(t.z, t.w);
+          const cacfe_f2 zr = cacfe_pk(re[s0], re[s1]), zi = cacfe_pk(im[s0], im[s1]);
+          const cacfe_f2 yr = cacfe_sub2(cacfe_mul2(zr, tr), cacfe_mul2(zi, ti));
+          const cacfe_f2 yi = cacfe_fma2(zr, ti, cacfe_mul2(zi, tr));
+          re[s0] = cacfe_lo(yr);
+          re[s1] = cacfe_hi(yr);
+          im[s0] = cacfe_lo(yi);
+          im[s1] = cacfe_hi(yi);
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = re[CACFE_FFT64_SLOT(k1)];
+        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = re[k1];
         group_barrier(1 + g, 64);
         {
           const float4* row = reinterpret_cast<const float4*>(ex + j * kHalfStride);
@@ -258,9 +267,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           }
         }
         group_barrier(1 + g, 64);
-        // re[] now holds stage-2 inputs in natural order while im[] still holds stage-1 outputs in slot order
+        // re[] now holds stage-2 inputs while im[] still holds stage-1 outputs
 #pragma unroll
-        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = im[CACFE_FFT64_SLOT(k1)];
+        for (int k1 = 0; k1 < 64; ++k1) ex[k1 * kHalfStride + t64] = im[k1];
         group_barrier(1 + g, 64);
         {
           const float4* row = reinterpret_cast<const float4*>(ex + j * kHalfStride);
@@ -277,26 +286,29 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
 
-    // ---- split the two frames, power: bin k = j + 64 q goes to pbuf[k] --------------------------------------------------
-    const bool row0 = j == 0;
+    // ---- split the two frames, power: bin k = j + 64 q goes to pbuf[k] as (4 |XA|^2, 4 |XB|^2) -------------------------
+    // (the 1/4 of  XA = (Z[k] + conj Z[N-k]) / 2  is folded into the mel weights, mel_jobs.h)
+    {
+      const bool row0 = j == 0;
+      float2* prow = pbuf + j;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      // Z[N-k]: thread 64-j holds it in slot 63-q; row 0 pairs with its own slot (64-q)&63
-      const float sr = __shfl_sync(kFullMask, re[CACFE_FFT64_SLOT(63 - q)], plane);
-      const float si = __shfl_sync(kFullMask, im[CACFE_FFT64_SLOT(63 - q)], plane);
-      const float pr = row0 ? re[CACFE_FFT64_SLOT((64 - q) & 63)] : sr;
-      const float pi = row0 ? im[CACFE_FFT64_SLOT((64 - q) & 63)] : si;
-      const float zr = re[CACFE_FFT64_SLOT(q)], zi = im[CACFE_FFT64_SLOT(q)];
-      const float ar = zr + pr, ai = zi - pi;   // 2 XA
-      const float br = zr - pr, bi = zi + pi;   // 2i XB
-      const int k = j + 64 * q;  // bin -> 16-byte chunk k >> 1, swizzled (mel_jobs.h)
-      pbuf[2 * mel_swizzle(k >> 1) + (k & 1)] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+      for (int q = 0; q < NQ; ++q) {
+        // Z[N-k]: thread 64-j holds it in slot 63-q; row 0 pairs with its own slot (64-q)&63
+        const float sr = __shfl_sync(kFullMask, re[63 - q], plane);
+        const float si = __shfl_sync(kFullMask, im[63 - q], plane);
+        const float pr = row0 ? re[(64 - q) & 63] : sr;
+        const float pi = row0 ? im[(64 - q) & 63] : si;
+        const float zr = re[q], zi = im[q];
+        const float ar = zr + pr, ai = zi - pi;   // 2 XA
+        const float br = zr - pr, bi = zi + pi;   // 2i XB
+        prow[64 * q] = make_float2(fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
+      }
     }
     group_barrier(1 + g, 64);
     if (a.power == 1) {  // magnitude (stored-spectrogram convention, tfdataset.py:1085-1088): rolled, off the hot path
-      for (int k = t64; k < 64 * NQ; k += 64) {  // element-wise: the swizzle does not matter
+      for (int k = t64; k < 64 * NQ; k += 64) {
         const float2 v = pbuf[k];
-        pbuf[k] = make_float2(sqrtf(v.x), sqrtf(v.y));
+        pbuf[k] = make_float2(2.0f * sqrtf(v.x), 2.0f * sqrtf(v.y));  // 4 |X|, same weight scale as the power case
       }
       group_barrier(1 + g, 64);
     }
@@ -315,13 +327,14 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         const int nq = mj.nq[sg];
         if (nq == 0) continue;  // uniform
         const int d = s_desc[sg * 64 + t64];
-        int c = (d >> 8) & 0xffff;
+        const float4* pp = p4 + ((d >> 8) & 0xffff);   // first 16-byte chunk: (A[k], B[k], A[k+1], B[k+1])
         float acc_a = 0.0f, acc_b = 0.0f;
+        float4 wv = wq[0], p01 = pp[0], p23 = pp[1];
 #pragma unroll 1
-        for (int i = 0; i < nq; ++i, c += 2, wq += 64) {
-          const float4 wv = *wq;
-          const float4 p01 = p4[mel_swizzle(c)];      // (A[k], B[k], A[k+1], B[k+1])
-          const float4 p23 = p4[mel_swizzle(c + 1)];
+        for (int i = 0; i < nq; ++i) {
+          wq += 64;
+          pp += 2;
+          const float4 wn = wq[0], n01 = pp[0], n23 = pp[1];  // next quad (one past the end on the last trip: in bounds)
           acc_a = fmaf(wv.x, p01.x, acc_a);
           acc_b = fmaf(wv.x, p01.y, acc_b);
           acc_a = fmaf(wv.y, p01.z, acc_a);
@@ -330,6 +343,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.z, p23.y, acc_b);
           acc_a = fmaf(wv.w, p23.z, acc_a);
           acc_b = fmaf(wv.w, p23.w, acc_b);
+          wv = wn;
+          p01 = n01;
+          p23 = n23;
         }
         if (sg == mj.split_seg) {  // uniform: lanes 2i / 2i+1 hold the two halves of one band
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);

@@ -5,6 +5,7 @@
 // share the bands out so that every thread sees about the same number of taps:
 //   segment s < n_mels / 64 : band 64 s + t (s even) or 64 s + 63 - t (s odd)      -- widths grow with the band index
 //   last, short segment     : (n_mels % 64 <= 32) each band is cut in two halves for lanes 2i / 2i+1, summed by shuffle
+// The weights are stored times 1/4 (exact): the kernel keeps 4 |X|^2 (or 4 |X|), see k_frontend_v3.cuh.
 // Taps are consumed four bins at a time ("quads": one 16-byte weight load, two 16-byte power loads, 8 FMAs).  Every
 // thread of a segment runs the same number of quads; the surplus taps carry weight 0.
 // Plain C++ (no CUDA): tests/emul exercises this builder against the dense bank on the CPU.
@@ -100,7 +101,7 @@ inline MelJobs build_mel_jobs(const float* bank, int n_mels, int n_bins, int n_c
           for (int e = 0; e < 4; ++e) {
             const int bin = 2 * c0 + 4 * i + e;
             if (bin >= j.ka && bin <= j.kb)
-              J.w[(((size_t)(qbase + i)) * 64 + t) * 4 + e] = bank[(size_t)j.m * n_bins + bin];
+              J.w[(((size_t)(qbase + i)) * 64 + t) * 4 + e] = 0.25f * bank[(size_t)j.m * n_bins + bin];  // exact
           }
       }
       J.desc[s * 64 + t] = (j.valid ? (j.m & 0xff) : 0) | (c0 << 8) | ((j.valid ? 1 : 0) << 24) | ((j.stores ? 1 : 0) << 25);
@@ -111,11 +112,5 @@ inline MelJobs build_mel_jobs(const float* bank, int n_mels, int n_bins, int n_c
   return J;
 }
 
-// 16-byte chunk c of the power buffer lives at chunk mel_swizzle(c): lanes whose bands start a few chunks apart
-// land in different bank groups.
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-inline int mel_swizzle(int c) { return c ^ ((c >> 3) & 7); }
 
 }  // namespace cacfe

@@ -56,13 +56,11 @@ extern "C" int mel_jobs_emul(const float* bank, int n_mels, int n_bins, int n_ch
   const MelJobs J = build_mel_jobs(bank, n_mels, n_bins, n_chunks);
   if (!J.ok) return 1;
   *total_quads = J.total_quads;
-  // the kernel's power buffer: float2 (A, B) per bin, 16-byte chunks swizzled
+  // the kernel's power buffer: float2 (4 |XA|^2, 4 |XB|^2) per bin (the weights carry the 1/4)
   std::vector<float> pbuf((size_t)4 * n_chunks, 0.0f);
   for (int k = 0; k < 2 * n_chunks; ++k) {
-    const int idx = 2 * mel_swizzle(k >> 1) + (k & 1);
-    if (idx < 0 || idx >= 2 * n_chunks) return 2;
-    pbuf[2 * idx] = power[k];
-    pbuf[2 * idx + 1] = 2.0f * power[k];
+    pbuf[2 * k] = 4.0f * power[k];
+    pbuf[2 * k + 1] = 8.0f * power[k];
   }
   std::vector<int> written(n_mels, 0);
   int qbase = 0;
@@ -77,8 +75,8 @@ extern "C" int mel_jobs_emul(const float* bank, int n_mels, int n_bins, int n_ch
       for (int i = 0; i < nq; ++i, c += 2) {
         if (c < 0 || c + 1 >= n_chunks) return 3;
         const float* wv = &J.w[(((size_t)(qbase + i)) * 64 + t) * 4];
-        const float* p01 = &pbuf[4 * mel_swizzle(c)];
-        const float* p23 = &pbuf[4 * mel_swizzle(c + 1)];
+        const float* p01 = &pbuf[4 * c];
+        const float* p23 = &pbuf[4 * (c + 1)];
         acc_a[t] = std::fmaf(wv[0], p01[0], acc_a[t]);
         acc_b[t] = std::fmaf(wv[0], p01[1], acc_b[t]);
         acc_a[t] = std::fmaf(wv[1], p01[2], acc_a[t]);
