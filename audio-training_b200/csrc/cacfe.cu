@@ -227,6 +227,7 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
       if (s_lo < 0 && -s_lo >= s_lo + p->kv.tile_len) reflect_fits = false;
     }
   p->v3_ok = p->frontend_ok && p->jobs.ok && p->kv.total <= (size_t)prop.sharedMemPerBlockOptin &&
+             p->kv.tile_pad <= cacfe::kNormIters * cacfe::kVThreads * 4 &&
              cfg->n_samples % 4 == 0 && reflect_fits;
   if (const char* v = std::getenv("CACFE_K1_VARIANT")) p->variant = std::atoi(v);
 

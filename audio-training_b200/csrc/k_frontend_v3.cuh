@@ -30,6 +30,7 @@ namespace cacfe {
 constexpr int kVGroups = 6;
 constexpr int kVThreads = kVGroups * 64;
 constexpr int kVTileFrames = 2 * kVGroups;
+constexpr int kNormIters = 6;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
 
 struct VSmem {
   int tile_len, tile_pad, mel_quads;
@@ -45,7 +46,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
   s.off_win = o;    o += sizeof(float) * 2052;
   s.off_tile = o;   o += sizeof(float) * s.tile_pad * 2;
   s.off_exch = o;   o += sizeof(float) * kHalfFloats * kVGroups;
-  s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads + 1);   // + 1: the mel loop prefetches one quad ahead
+  s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads > 0 ? mel_quads : 1);
   s.off_desc = o;   o += sizeof(int) * 64 * kMelMaxSeg;
   s.off_sync = o;   o += 96;                         // full/norm/pre mbarriers, done counters, normalisation pairs
   s.total = o;
@@ -119,23 +120,22 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       sc = 2.0f / nrm.x;      // range 0 -> inf -> (x - mn) * inf = NaN: constant clips give NaN features (Q1)
       of = -0.999998f;
     }
+    // s_lo and n_samples are multiples of 4: a 16-byte group of samples lies entirely inside or outside the clip
     float4* t4 = reinterpret_cast<float4*>(tile);
     const int n4 = L.tile_pad >> 2;
-    for (int e = tid; e < n4; e += kVThreads) {
-      const int p = s_lo + 4 * e;
-      float4 v = t4[e];
-      if (p >= 0 && p + 3 < a.n_samples) {
-        v.x = fmaf(v.x - mn, sc, of);
-        v.y = fmaf(v.y - mn, sc, of);
-        v.z = fmaf(v.z - mn, sc, of);
-        v.w = fmaf(v.w - mn, sc, of);
-      } else {
-        v.x = (p >= 0 && p < a.n_samples) ? fmaf(v.x - mn, sc, of) : 0.0f;
-        v.y = (p + 1 >= 0 && p + 1 < a.n_samples) ? fmaf(v.y - mn, sc, of) : 0.0f;
-        v.z = (p + 2 >= 0 && p + 2 < a.n_samples) ? fmaf(v.z - mn, sc, of) : 0.0f;
-        v.w = (p + 3 >= 0 && p + 3 < a.n_samples) ? fmaf(v.w - mn, sc, of) : 0.0f;
+    const int e_lo = s_lo < 0 ? (-s_lo) >> 2 : 0, e_hi = (a.n_samples - s_lo) >> 2;
+    const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
+#pragma unroll
+    for (int u = 0; u < kNormIters; ++u) {
+      const int e = tid + u * kVThreads;
+      if (e < n4) {
+        const float4 v = t4[e];
+        const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v.x, v.y), mn2), sc2, of2);
+        const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v.z, v.w), mn2), sc2, of2);
+        const bool inside = e >= e_lo && e < e_hi;
+        t4[e] = inside ? make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi))
+                       : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
-      t4[e] = v;
     }
     if (a.reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
       __syncwarp();
@@ -181,8 +181,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   {
     for (int i = tid; i < 2048; i += kVThreads) s_tw4[i] = mj.tw4[i];
     for (int i = tid; i < 2049; i += kVThreads) s_win[i] = a.win[i];
-    for (int i = tid; i < 64 * (mj.total_quads + 1); i += kVThreads)
-      s_melw[i] = i < 64 * mj.total_quads ? mj.w[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int i = tid; i < 64 * mj.total_quads; i += kVThreads) s_melw[i] = mj.w[i];
     for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
   }
   __syncthreads();
@@ -329,12 +328,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         const int d = s_desc[sg * 64 + t64];
         const float4* pp = p4 + ((d >> 8) & 0xffff);   // first 16-byte chunk: (A[k], B[k], A[k+1], B[k+1])
         float acc_a = 0.0f, acc_b = 0.0f;
-        float4 wv = wq[0], p01 = pp[0], p23 = pp[1];
 #pragma unroll 1
-        for (int i = 0; i < nq; ++i) {
-          wq += 64;
-          pp += 2;
-          const float4 wn = wq[0], n01 = pp[0], n23 = pp[1];  // next quad (one past the end on the last trip: in bounds)
+        for (int i = 0; i < nq; ++i, wq += 64, pp += 2) {
+          const float4 wv = wq[0], p01 = pp[0], p23 = pp[1];
           acc_a = fmaf(wv.x, p01.x, acc_a);
           acc_b = fmaf(wv.x, p01.y, acc_b);
           acc_a = fmaf(wv.y, p01.z, acc_a);
@@ -343,9 +339,6 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.z, p23.y, acc_b);
           acc_a = fmaf(wv.w, p23.z, acc_a);
           acc_b = fmaf(wv.w, p23.w, acc_b);
-          wv = wn;
-          p01 = n01;
-          p23 = n23;
         }
         if (sg == mj.split_seg) {  // uniform: lanes 2i / 2i+1 hold the two halves of one band
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
