@@ -271,10 +271,14 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
-  if (e == cudaSuccess && p->v3_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_v3_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
-  if (e == cudaSuccess && p->v3_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_v3_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
+  if (e == cudaSuccess && p->v3_ok) {
+    const void* kernels[4] = {(const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM>,
+                              (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC>,
+                              (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM>,
+                              (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC>};
+    for (int q = 0; q < 4 && e == cudaSuccess; ++q)
+      e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
+  }
   if (e != cudaSuccess) {
     cacfe_plan_destroy(p);
     return fail(CACFE_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -509,10 +513,15 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     a.tiles_per_clip = (p->n_frames + cacfe::kVTileFrames - 1) / cacfe::kVTileFrames;
     const long long tiles = (long long)B * a.tiles_per_clip;
     const unsigned ctas = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);  // one persistent CTA per SM
-    if (p->nq <= 15)
-      cacfe::stft_mel_v3_kernel<15><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    const bool btm = layout == CACFE_LAYOUT_BTM;
+    if (p->nq <= 15 && btm)
+      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    else if (p->nq <= 15)
+      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    else if (btm)
+      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else
-      cacfe::stft_mel_v3_kernel<33><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
   } else if (stream) {
     a.bw_in_smem = p->ks.bw_in_smem;
     const unsigned ctas = (unsigned)(grid < p->sm_count ? grid : p->sm_count);  // one persistent CTA per SM

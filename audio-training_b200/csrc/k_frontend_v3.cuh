@@ -62,7 +62,7 @@ struct MelArgs {
   int split_seg, total_quads;
 };
 
-template <int NQ>
+template <int NQ, int LAYOUT>
 __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const FrontendArgs a, const MelArgs mj,
                                                                       const int total_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -104,11 +104,8 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   };
 
   // Every warp normalises its slice of tile i in place (and writes the padding), then arrives on s_norm[i&1].
-  auto normalise_tile = [&](int i) {
+  auto normalise_tile = [&](int i, int b, int t0) {
     const int s = i & 1;
-    const int w = (int)blockIdx.x + i * (int)gridDim.x;
-    const int b = w / a.tiles_per_clip;
-    const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
     const int s_lo = a.origin + a.hop * t0;
     float* tile = s_tile + (size_t)s * L.tile_pad;
     const uint32_t parity = (uint32_t)((i >> 1) & 1);
@@ -189,7 +186,11 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     if (my_tiles > 0) issue_tile(0);
     if (my_tiles > 1) issue_tile(1);
   }
-  if (my_tiles > 0) normalise_tile(0);
+  // tile coordinates (clip, first frame) advance by gridDim.x tiles per trip: kept incrementally, no division in the loop
+  const int step_b = (int)gridDim.x / a.tiles_per_clip, step_t = ((int)gridDim.x % a.tiles_per_clip) * kVTileFrames;
+  const int wrap_t = a.tiles_per_clip * kVTileFrames;
+  int b = (int)blockIdx.x / a.tiles_per_clip, t0 = ((int)blockIdx.x % a.tiles_per_clip) * kVTileFrames;
+  if (my_tiles > 0) normalise_tile(0, b, t0);
 
   float* ex = s_exch + g * kHalfFloats;
   float2* pbuf = reinterpret_cast<float2*>(ex);  // (power A, power B) per bin; aliases the exchange tile
@@ -200,15 +201,20 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   // The six groups run free: there is no CTA-wide barrier in the loop, only the two mbarrier hand-overs per tile.
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i & 1;
-    const int w = (int)blockIdx.x + i * (int)gridDim.x;
-    const int b = w / a.tiles_per_clip;
-    const int t0 = (w - b * a.tiles_per_clip) * kVTileFrames;
     float* tile = s_tile + (size_t)s * L.tile_pad;
+    int b_next = b + step_b, t_next = t0 + step_t;
+    if (t_next >= wrap_t) {
+      t_next -= wrap_t;
+      ++b_next;
+    }
 
-    if (i + 1 < my_tiles) normalise_tile(i + 1);   // buffer s^1: its TMA was issued when tile i-1 had been read by all
+    if (i + 1 < my_tiles) normalise_tile(i + 1, b_next, t_next);   // buffer s^1: its TMA was issued when tile i-1 had been read by all
     mbar_wait(smem_u32(&s_norm[s]), (uint32_t)((i >> 1) & 1));
 
     const int ta = t0 + 2 * g;
+    const int b_cur = b;
+    b = b_next;
+    t0 = t_next;
     if (ta >= a.n_frames) {  // group-uniform
       release_tile(i);
       continue;
@@ -314,17 +320,13 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
 
     // ---- banded mel projection (mel_jobs.h), both frames of the pair per thread, straight to global -------------------
     {
-      const size_t row = (size_t)b * a.n_frames + ta;
-      const long long m_stride = a.layout == LAYOUT_BTM ? 1 : (long long)a.n_frames * a.channels;
-      const int f_stride = a.layout == LAYOUT_BTM ? a.n_mels : a.channels;
-      float* obase = a.layout == LAYOUT_BTM ? a.out + row * a.n_mels
-                                            : a.out + ((size_t)b * a.n_mels * a.n_frames + ta) * a.channels;
       const float4* p4 = reinterpret_cast<const float4*>(pbuf);
       const float4* wq = s_melw + t64;
+      float ra[kMelMaxSeg], rb[kMelMaxSeg];
+      int dsc[kMelMaxSeg];
 #pragma unroll
       for (int sg = 0; sg < kMelMaxSeg; ++sg) {
-        const int nq = mj.nq[sg];
-        if (nq == 0) continue;  // uniform
+        const int nq = mj.nq[sg];                      // uniform
         const int d = s_desc[sg * 64 + t64];
         const float4* pp = p4 + ((d >> 8) & 0xffff);   // first 16-byte chunk: (A[k], B[k], A[k+1], B[k+1])
         float acc_a = 0.0f, acc_b = 0.0f;
@@ -344,14 +346,31 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
           acc_b += __shfl_xor_sync(kFullMask, acc_b, 1);
         }
-        if ((d >> 25) & 1) {
-          float* o = obase + (d & 0xff) * m_stride;
-#pragma unroll 1
-          for (int ch = 0; ch < a.channels; ++ch) {
-            o[ch] = acc_a;
-            if (store_b) o[f_stride + ch] = acc_b;
+        ra[sg] = acc_a;
+        rb[sg] = acc_b;
+        dsc[sg] = d;
+      }
+      if (LAYOUT == LAYOUT_BTM) {  // [b][t][m]: one coalesced row per frame
+        float* o = a.out + ((size_t)b_cur * a.n_frames + ta) * a.n_mels;
+#pragma unroll
+        for (int sg = 0; sg < kMelMaxSeg; ++sg)
+          if ((dsc[sg] >> 25) & 1) {
+            o[dsc[sg] & 0xff] = ra[sg];
+            if (store_b) o[a.n_mels + (dsc[sg] & 0xff)] = rb[sg];
           }
-        }
+      } else {                     // [b][m][t][c]
+        float* obase = a.out + ((size_t)b_cur * a.n_mels * a.n_frames + ta) * a.channels;
+        const size_t m_stride = (size_t)a.n_frames * a.channels;
+#pragma unroll
+        for (int sg = 0; sg < kMelMaxSeg; ++sg)
+          if ((dsc[sg] >> 25) & 1) {
+            float* o = obase + (dsc[sg] & 0xff) * m_stride;
+#pragma unroll 1
+            for (int ch = 0; ch < a.channels; ++ch) {
+              o[ch] = ra[sg];
+              if (store_b) o[a.channels + ch] = rb[sg];
+            }
+          }
       }
     }
     // (the next trip's exchange stores come after release_tile's group barrier: the powers have been consumed by then)
