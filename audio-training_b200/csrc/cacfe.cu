@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,6 +44,8 @@ int fail(int code, const char* fmt, ...) {
 inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
 constexpr int kMaxSplits = 16;
+
+std::mutex g_upload_gate[16];  // one per device: see cacfe_hostpipe_run
 
 }  // namespace
 
@@ -810,7 +813,12 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
   a.extremes = h->d_extremes;
   const bool global = q->norm_scope == CACFE_NORM_TENSOR;
   // phase 1: per chunk H2D -> min/max -> mel [b][T][M] (device resident) -> PCEN reduce (or the final PCEN
-  // when the scope allows the chunk to finish on its own)
+  // when the scope allows the chunk to finish on its own).
+  // With the tensor-global scope a run is an upload phase followed by a download phase; several pipes driven from
+  // several host threads (the way to keep both PCIe directions busy) must not split the upload link between them,
+  // so the upload phase of a device is taken by one pipe at a time.
+  std::unique_lock<std::mutex> upload_gate;
+  if (global) upload_gate = std::unique_lock<std::mutex>(g_upload_gate[p->device & 15]);
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
     cudaStream_t st = h->stream[s];
@@ -840,6 +848,10 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
     CUDA_TRY(cudaEventRecord(h->done[s], st));
   }
   if (global) {
+    // the uploads are in flight: wait for the last one of each stream, then let the next pipe upload
+    CUDA_TRY(cudaEventSynchronize(h->done[0]));
+    if (nchunks > 1) CUDA_TRY(cudaEventSynchronize(h->done[1]));
+    upload_gate.unlock();
     // phase 2: tensor-global extremes need every chunk (tfpcen.py:105-110)
     CUDA_TRY(cudaStreamWaitEvent(h->stream[0], h->done[1], 0));
     cacfe::minmax_finalize_kernel<<<1, 256, 0, h->stream[0]>>>(h->d_partial, B * g.gx, h->d_extremes);
