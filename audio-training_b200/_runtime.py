@@ -40,6 +40,7 @@ class FrontendConfig:
     channels: int = 3
     out_layout: str = "bmtc"
     normalize: bool = False
+    mel_impl: str = "banded_fp32"   # "tc_3xtf32": tcgen05 banded 3xTF32 GEMM for mel_from_spectrogram (path C)
 
     def with_(self, **kw):
         return replace(self, **kw)
@@ -74,7 +75,7 @@ class Plan:
         cfg.n_mels, cfg.fmin, cfg.fmax, cfg.break_freq = config.n_mels, config.fmin, config.fmax, config.break_freq
         cfg.power, cfg.channels = config.power, config.channels
         cfg.out_layout = _LAYOUT[config.out_layout]
-        cfg.mel_impl = _lib.MEL_BANDED_FP32
+        cfg.mel_impl = {"banded_fp32": _lib.MEL_BANDED_FP32, "tc_3xtf32": _lib.MEL_TC_3XTF32}[config.mel_impl]
         cfg.normalize = 1 if config.normalize else 0
         self._bank_keepalive = None
         if filterbank is not None:

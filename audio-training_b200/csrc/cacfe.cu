@@ -19,6 +19,7 @@
 #include "k_frontend_stream.cuh"
 #include "k_frontend_v3.cuh"
 #include "k_melspec.cuh"
+#include "k_melspec_tc.cuh"
 #include "k_pcen.cuh"
 
 namespace {
@@ -65,6 +66,11 @@ struct cacfe_plan {
   cacfe::MelJobs jobs;
   float4* d_mel_w = nullptr;
   float4* d_tw4 = nullptr;
+  // tcgen05 stored-spectrogram path (CACFE_MEL_TC_3XTF32)
+  bool tc_ok = false;
+  std::vector<cacfe::MelTcChunk> tc_chunks;
+  float* d_tc_w = nullptr;
+  cacfe::MelTcChunk* d_tc_chunks = nullptr;
   int* d_mel_desc = nullptr;
   bool stream_ok = false;
   bool v3_ok = false;
@@ -140,8 +146,8 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (cfg->framing < 0 || cfg->framing > 3) return fail(CACFE_EINVAL, "plan_create: unknown framing");
   if (cfg->framing == CACFE_FRAME_CENTER_REFLECT && cfg->n_samples <= cfg->n_fft / 2)
     return fail(CACFE_EINVAL, "plan_create: reflect padding needs n_samples > n_fft/2");
-  if (cfg->mel_impl != CACFE_MEL_BANDED_FP32)
-    return fail(CACFE_EINVAL, "plan_create: mel_impl %d not available in this build", cfg->mel_impl);
+  if (cfg->mel_impl != CACFE_MEL_BANDED_FP32 && cfg->mel_impl != CACFE_MEL_TC_3XTF32)
+    return fail(CACFE_EINVAL, "plan_create: unknown mel_impl %d", cfg->mel_impl);
 
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -207,6 +213,53 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   p->nq = hi / 64 + 1;
   if (bw.empty()) bw.push_back(0.0f);
 
+  // tensor-core form for the stored-spectrogram path: 32-bin chunks, each with the 16-aligned run of bands it touches,
+  // weights split hi (TF32: low 13 mantissa bits cleared) + lo and packed in the UMMA canonical K-major layout
+  // [k / 4][n / 8][n % 8][k % 4] (k_melspec_tc.cuh)
+  std::vector<float> tc_w;
+  p->tc_ok = cfg->n_mels % 16 == 0 && cfg->n_mels <= 256;
+  for (int k0 = lo & ~3; p->tc_ok && k0 <= hi; k0 += cacfe::kTcK) {
+    int m_lo = cfg->n_mels, m_hi = -1;
+    for (int m = 0; m < cfg->n_mels; ++m)
+      for (int k = k0; k < k0 + cacfe::kTcK && k < p->n_bins; ++k)
+        if (p->bank[(size_t)m * p->n_bins + k] != 0.0f) {
+          m_lo = std::min(m_lo, m);
+          m_hi = std::max(m_hi, m);
+        }
+    if (m_hi < 0) continue;  // no band touches these bins
+    cacfe::MelTcChunk ch;
+    ch.k0 = k0;
+    ch.n0 = m_lo & ~15;
+    ch.nc = ((m_hi + 16) & ~15) - ch.n0;
+    ch.w_ofs = (int)tc_w.size();
+    if (ch.nc > cacfe::kTcMaxN) {
+      p->tc_ok = false;
+      break;
+    }
+    const size_t block = (size_t)ch.nc * cacfe::kTcK;
+    tc_w.resize(tc_w.size() + 2 * block, 0.0f);
+    for (int n = 0; n < ch.nc; ++n)
+      for (int kk = 0; kk < cacfe::kTcK; ++kk) {
+        const int k = k0 + kk, m = ch.n0 + n;
+        const float w = (k < p->n_bins && m < cfg->n_mels) ? p->bank[(size_t)m * p->n_bins + k] : 0.0f;
+        uint32_t bits;
+        std::memcpy(&bits, &w, 4);
+        bits &= 0xffffe000u;
+        float w_hi;
+        std::memcpy(&w_hi, &bits, 4);
+        const size_t idx = (size_t)(kk / 4) * (ch.nc / 8) * 32 + (size_t)(n / 8) * 32 + (n % 8) * 4 + (kk % 4);
+        tc_w[ch.w_ofs + idx] = w_hi;
+        tc_w[ch.w_ofs + block + idx] = w - w_hi;
+      }
+    p->tc_chunks.push_back(ch);
+  }
+  if (p->tc_chunks.empty()) p->tc_ok = false;
+  if (cfg->mel_impl == CACFE_MEL_TC_3XTF32 && !p->tc_ok) {
+    delete p;
+    return fail(CACFE_EINVAL, "plan_create: the tensor-core mel path needs n_mels %% 16 == 0, n_mels <= 256 and at most %d "
+                "bands per 32-bin chunk", cacfe::kTcMaxN);
+  }
+
   // The fused raw->mel kernel exists for n_fft = 4096 (the reference's only shipped configuration); other sizes
   // get a plan for the spectrogram / PCEN / compression entry points and cacfe_frontend refuses them.
   p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
@@ -271,6 +324,11 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
   if (e == cudaSuccess && p->stream_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
+  if (e == cudaSuccess && p->tc_ok) e = upload((void**)&p->d_tc_w, tc_w.data(), tc_w.size() * sizeof(float));
+  if (e == cudaSuccess && p->tc_ok)
+    e = upload((void**)&p->d_tc_chunks, p->tc_chunks.data(), p->tc_chunks.size() * sizeof(cacfe::MelTcChunk));
+  if (e == cudaSuccess && p->tc_ok)
+    e = cudaFuncSetAttribute(cacfe::melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kTcSmemBytes);
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
@@ -299,6 +357,8 @@ void cacfe_plan_destroy(cacfe_plan* p) {
   cudaFree(p->d_band_start);
   cudaFree(p->d_band_ofs);
   cudaFree(p->d_mel_w);
+  cudaFree(p->d_tc_w);
+  cudaFree(p->d_tc_chunks);
   cudaFree(p->d_tw4);
   cudaFree(p->d_mel_desc);
   delete p;
@@ -560,6 +620,24 @@ int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, in
   if (!p || !spec || !feat) return fail(CACFE_EINVAL, "mel_from_spectrogram: null argument");
   if (B < 1 || B > 65535 || T < 1) return fail(CACFE_ESHAPE, "mel_from_spectrogram: B=%d T=%d", B, T);
   CUDA_TRY(cudaSetDevice(p->device));
+  if (p->cfg.mel_impl == CACFE_MEL_TC_3XTF32) {  // tcgen05 banded 3xTF32 GEMM
+    cacfe::MelTcArgs t;
+    t.spec = spec;
+    t.out = feat;
+    t.wpk = p->d_tc_w;
+    t.chunks = p->d_tc_chunks;
+    t.n_chunks = (int)p->tc_chunks.size();
+    t.n_bins = p->n_bins;
+    t.T = T;
+    t.n_mels = p->cfg.n_mels;
+    t.power = p->cfg.power;
+    t.channels = p->cfg.channels;
+    t.layout = p->cfg.out_layout;
+    t.tiles_per_clip = (T + cacfe::kTcM - 1) / cacfe::kTcM;
+    const long long grid = (long long)B * t.tiles_per_clip;
+    cacfe::melspec_tc_kernel<<<(unsigned)grid, cacfe::kTcThreads, cacfe::kTcSmemBytes, (cudaStream_t)stream>>>(t);
+    return check_launch(p, "mel_from_spectrogram (tensor core)");
+  }
   cacfe::MelSpecArgs a;
   a.spec = spec;
   a.out = feat;

@@ -17,7 +17,6 @@
 namespace cacfe {
 
 constexpr int kMelMaxSeg = 3;
-constexpr int kMelMaxQuads = 8;   // quads per thread and segment the kernel unrolls (32 bins: bands up to ~30 taps)
 
 struct MelJobs {
   bool ok = false;
@@ -84,7 +83,7 @@ inline MelJobs build_mel_jobs(const float* bank, int n_mels, int n_bins, int n_c
       const int c0 = j.ka >> 1;
       q = std::max(q, (j.kb - 2 * c0 + 1 + 3) / 4);
     }
-    if (2 * q > n_chunks || q > kMelMaxQuads) return J;
+    if (2 * q > n_chunks) return J;
     J.nq[s] = q;
     J.total_quads += q;
   }

@@ -25,6 +25,12 @@ import sys
 import threading
 import time
 
+# The reference arm uses every host thread it can (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU path):
+# the thread-pool sizes are read when numpy / scipy load, so they are set before the import.
+if "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))

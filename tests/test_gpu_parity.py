@@ -211,6 +211,25 @@ def test_path_c(oracle, golden, xn, bank):
     check(oracle, small, oracle.mel_spec(mag[:1025], 48000, 2048, 278, 96, 100, 11000, 1000, 1), what="mel_spec 2048")
 
 
+@pytest.mark.parametrize("power,layout,channels", [(1, "bmtc", 1), (2, "bmtc", 3), (1, "btm", 1)])
+def test_path_c_tensor_core(oracle, xn, bank, power, layout, channels):
+    """tcgen05 banded 3xTF32 GEMM (k_melspec_tc.cuh) against the f64 oracle and against the banded FP32 kernel."""
+    mags = np.stack([np.abs(oracle.stft_librosa(xn[i % 2], dtype=np.float32)).astype(np.float32) for i in range(3)])
+    mags[2] *= 37.5                                                    # another scale: the hi/lo split is relative
+    spec = torch.from_numpy(mags).cuda()
+    cfg = rt.FrontendConfig(power=power, channels=channels, out_layout=layout, mel_impl="tc_3xtf32")
+    tc = rt.Plan(cfg, 0, bank).mel_from_spectrogram(spec)
+    ref = rt.Plan(cfg.with_(mel_impl="banded_fp32"), 0, bank).mel_from_spectrogram(spec)
+    assert tc.shape == ref.shape
+    want = np.stack([oracle.mel_from_spectrogram(m, bank, power=power)[..., 0] for m in mags])   # [B, M, T]
+    got = tc.cpu().numpy()
+    got = np.swapaxes(got, 1, 2) if layout == "btm" else got[..., 0]
+    check(oracle, got, want, what="tensor-core path C vs f64 oracle")
+    check(oracle, tc, ref.cpu().numpy(), 2.0, what="tensor-core vs banded FP32")
+    if channels == 3:
+        assert torch.equal(tc[..., 0], tc[..., 2])
+
+
 # ------------------------------------------------------------------------------------------------ PCEN
 def test_ema_bit_exact(oracle, golden):
     x = np.swapaxes(golden["path_a"], 1, 2).copy()
