@@ -634,6 +634,7 @@ int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, in
     t.channels = p->cfg.channels;
     t.layout = p->cfg.out_layout;
     t.tiles_per_clip = (T + cacfe::kTcM - 1) / cacfe::kTcM;
+    t.tile_frames = (T + t.tiles_per_clip - 1) / t.tiles_per_clip;
     const long long grid = (long long)B * t.tiles_per_clip;
     cacfe::melspec_tc_kernel<<<(unsigned)grid, cacfe::kTcThreads, cacfe::kTcSmemBytes, (cudaStream_t)stream>>>(t);
     return check_launch(p, "mel_from_spectrogram (tensor core)");

@@ -36,7 +36,7 @@ struct MelTcChunk {
 constexpr int kTcM = 128;          // frames per tile (UMMA M)
 constexpr int kTcK = 32;           // bins per chunk
 constexpr int kTcMaxN = 64;        // bands per chunk the plan accepts
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 2;          // 2 x 48 KB: two CTAs per SM
 constexpr int kTcProducers = 256;
 constexpr int kTcThreads = kTcProducers + 64;
 constexpr int kTcSboA = 128;                       // bytes between 8-frame groups of A (core matrices are contiguous)
@@ -52,6 +52,7 @@ struct MelTcArgs {
   const float* wpk;           // packed weights, see MelTcChunk
   const MelTcChunk* chunks;
   int n_chunks, n_bins, T, n_mels, power, channels, layout, tiles_per_clip;
+  int tile_frames;            // frames per tile (<= 128): T split evenly over the tiles (513 -> 5 x 103)
 };
 
 // ---- tcgen05 wrappers --------------------------------------------------------------------------------------------
@@ -79,7 +80,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kTcThreads, 1) melspec_tc_kernel(const MelTcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 2) melspec_tc_kernel(const MelTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) melspec_tc_kernel(const MelTcAr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.tiles_per_clip;
-  const int t0 = (blockIdx.x - b * a.tiles_per_clip) * kTcM;
+  const int t0 = (blockIdx.x - b * a.tiles_per_clip) * a.tile_frames;
+  const int t_end = min(t0 + a.tile_frames, a.T);
   const int tmem_cols = a.n_mels <= 32 ? 32 : a.n_mels <= 64 ? 64 : a.n_mels <= 128 ? 128 : 256;
 
   if (tid == 0) {
@@ -130,18 +132,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) melspec_tc_kernel(const MelTcAr
   if (warp < kTcProducers / 32) {
     // ---- producers: spectrogram chunk -> hi / lo operands in canonical layout ---------------------------------------
     const int t = tid & (kTcM - 1), kh = tid >> 7;       // frame inside the tile; this thread takes bins kh*16 .. +15
-    const bool t_ok = t0 + t < a.T;
+    const bool t_ok = t0 + t < t_end;
     const float* col = a.spec + (size_t)b * a.n_bins * a.T + t0 + t;
     const uint32_t a_off = (uint32_t)((t >> 3) * kTcSboA + (t & 7) * 16);
-    for (int c = 0; c < a.n_chunks; ++c) {
-      const int s = c % kTcStages, use = c / kTcStages;
-      const int k0 = a.chunks[c].k0 + kh * 16;
-      float v[16];
+    auto load_chunk = [&](int c, float (&v)[16]) {
+      const int k0 = c < a.n_chunks ? a.chunks[c].k0 + kh * 16 : a.n_bins;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int k = k0 + i;
         v[i] = (t_ok && k < a.n_bins) ? ld_stream(col + (size_t)k * a.T) : 0.0f;
       }
+    };
+    float v[16], vn[16], vnn[16];
+    load_chunk(0, v);
+    load_chunk(1, vn);
+    for (int c = 0; c < a.n_chunks; ++c) {
+      const int s = c % kTcStages, use = c / kTcStages;
+      load_chunk(c + 2, vnn);  // two chunks of loads stay in flight while this one is split and stored
       if (use > 0) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((use - 1) & 1));
       unsigned char* sa = stage_base + (size_t)s * kTcStageBytes;
 #pragma unroll
@@ -160,6 +167,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) melspec_tc_kernel(const MelTcAr
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> visible to the tensor core
       mbar_arrive(smem_u32(&bar_ready[s]));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = vn[i];
+        vn[i] = vnn[i];
+      }
     }
   } else if (warp == 9) {
     // ---- filterbank loader ------------------------------------------------------------------------------------------
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) melspec_tc_kernel(const MelTcAr
           : "r"(taddr + c)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (t < a.T) {
+      if (t < t_end) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int m = c + i;

@@ -41,7 +41,8 @@ int main(int argc, char** argv) {
   cudaMemcpy(d_w, wpk.data(), wpk.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_ch, chunks.data(), chunks.size() * sizeof(MelTcChunk), cudaMemcpyHostToDevice);
   cudaMemset(d_out, 0xff, (size_t)B * nc * T * 4);
-  MelTcArgs a{d_spec, d_out, d_w, d_ch, (int)chunks.size(), n_bins, T, nc, 1, 1, 0, (T + kTcM - 1) / kTcM};
+  MelTcArgs a{d_spec, d_out, d_w, d_ch, (int)chunks.size(), n_bins, T, nc, 1, 1, 0, (T + kTcM - 1) / kTcM, 0};
+  a.tile_frames = (T + a.tiles_per_clip - 1) / a.tiles_per_clip;
   cudaFuncSetAttribute(melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
   melspec_tc_kernel<<<B * a.tiles_per_clip, kTcThreads, kTcSmemBytes>>>(a);
   cudaError_t e = cudaDeviceSynchronize();
