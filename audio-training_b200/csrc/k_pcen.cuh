@@ -39,7 +39,9 @@ __device__ __forceinline__ float pcen_point(float x, float m, const PcenArgs& a)
   // x / (eps + M)^gain  ==  x * 2^(-gain * log2(eps + M))      (MUFU lg2 / ex2)
   const float smooth = exp2f(-a.gain * __log2f(a.eps + m));
   const float y = fmaf(x, smooth, a.bias);
-  const float r = a.root_is_2 ? sqrtf(y) : exp2f(a.inv_root * __log2f(y));
+  // root 2 (the layer's initial value): y * rsqrt(y) -- one MUFU and one multiply, <= 2 ulp -- instead of the IEEE sqrt
+  // sequence; the pass is MUFU / issue bound, not HBM bound, until these are trimmed
+  const float r = a.root_is_2 ? (y > 0.0f ? y * rsqrtf(y) : 0.0f) : exp2f(a.inv_root * __log2f(y));
   return r - a.bias_pow;
 }
 
@@ -59,9 +61,12 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
     float* y = a.out + base;
     float scale = 1.0f, shift = 0.0f;
     if (MODE == PCEN_APPLY) {
-      const float2 e = a.extremes[a.per_clip_extremes ? clip : 0];
-      scale = e.x;  // pre-folded by pcen_finalize_kernel: out = 2 * ((v - min) / range) - 1
-      shift = e.y;
+      const float2 e = a.extremes[a.per_clip_extremes ? clip : 0];  // (range, min)
+      // 2 * ((v - min) / range) - 1 as one FMA with 2 / range: one division per thread instead of one per element
+      // (the pass is MUFU-bound; the result moves by <= 1 ulp of a value in [-1, 1])
+      scale = 2.0f / e.x;
+      if (e.x * scale < 2.0f) scale = __uint_as_float(__float_as_uint(scale) + 1u);  // range * scale >= 2: the maximum
+      shift = e.y;                                                                  // reaches 1 and is clamped to it
     }
     float m = x[0];  // initial state = inputs[:, 0, :]  (tfpcen.py:92)
     int t = 0;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
           mn = fminf(mn, p);
           mx = fmaxf(mx, p);
         } else {
-          if (MODE == PCEN_APPLY) p = 2.0f * ((p - shift) / scale) - 1.0f;
+          if (MODE == PCEN_APPLY) p = fminf(fmaf(p - shift, scale, -1.0f), 1.0f);
           y[(size_t)(t + u) * a.inner] = p;
         }
       }
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
         mn = fminf(mn, p);
         mx = fmaxf(mx, p);
       } else {
-        if (MODE == PCEN_APPLY) p = 2.0f * ((p - shift) / scale) - 1.0f;
+        if (MODE == PCEN_APPLY) p = fminf(fmaf(p - shift, scale, -1.0f), 1.0f);
         y[(size_t)t * a.inner] = p;
       }
     }
