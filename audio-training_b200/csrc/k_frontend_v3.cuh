@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const int s_lo = a.origin + a.hop * t0;
     float* tile = s_tile + (size_t)s * L.tile_pad;
     const uint32_t parity = (uint32_t)((i >> 1) & 1);
-    mbar_wait(smem_u32(&s_full[s]), parity);
+    mbar_wait_relaxed(smem_u32(&s_full[s]), parity);
     float mn = 0.0f, sc = 1.0f, of = 0.0f;
     if (a.norm != nullptr) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
       const float2 nrm = s_nrm[2 * s + (b & 1)];
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     }
 
     if (i + 1 < my_tiles) normalise_tile(i + 1, b_next, t_next);   // buffer s^1: its TMA was issued when tile i-1 had been read by all
-    mbar_wait(smem_u32(&s_norm[s]), (uint32_t)((i >> 1) & 1));
+    mbar_wait_relaxed(smem_u32(&s_norm[s]), (uint32_t)((i >> 1) & 1));
 
     const int ta = t0 + 2 * g;
     const int b_cur = b;
@@ -330,9 +330,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         const int d = s_desc[sg * 64 + t64];
         const float4* pp = p4 + ((d >> 8) & 0xffff);   // first 16-byte chunk: (A[k], B[k], A[k+1], B[k+1])
         float acc_a = 0.0f, acc_b = 0.0f;
-#pragma unroll 1
-        for (int i = 0; i < nq; ++i, wq += 64, pp += 2) {
-          const float4 wv = wq[0], p01 = pp[0], p23 = pp[1];
+        auto quad = [&](const float4 wv, const float4 p01, const float4 p23) {
           acc_a = fmaf(wv.x, p01.x, acc_a);
           acc_b = fmaf(wv.x, p01.y, acc_b);
           acc_a = fmaf(wv.y, p01.z, acc_a);
@@ -341,6 +339,17 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.z, p23.y, acc_b);
           acc_a = fmaf(wv.w, p23.z, acc_a);
           acc_b = fmaf(wv.w, p23.w, acc_b);
+        };
+        int i = 0;
+#pragma unroll 1
+        for (; i + 1 < nq; i += 2, wq += 128, pp += 4) {  // two quads per trip: six 16-byte loads in flight
+          const float4 w0 = wq[0], a0 = pp[0], a1 = pp[1], w1 = wq[64], b0 = pp[2], b1 = pp[3];
+          quad(w0, a0, a1);
+          quad(w1, b0, b1);
+        }
+        if (i < nq) {
+          quad(wq[0], pp[0], pp[1]);
+          wq += 64;
         }
         if (sg == mj.split_seg) {  // uniform: lanes 2i / 2i+1 hold the two halves of one band
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
