@@ -122,10 +122,20 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const int n4 = L.tile_pad >> 2;
     const int e_lo = s_lo < 0 ? (-s_lo) >> 2 : 0, e_hi = (a.n_samples - s_lo) >> 2;
     const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
+    if (e_lo == 0 && e_hi >= n4) {  // the whole tile lies inside the clip (41 of 43 tiles): no padding to write
 #pragma unroll
-    for (int u = 0; u < kNormIters; ++u) {
-      const int e = tid + u * kVThreads;
-      if (e < n4) {
+      for (int u = 0; u < kNormIters; ++u) {
+        const int e = tid + u * kVThreads;
+        if (e < n4) {
+          const float4 v = t4[e];
+          const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v.x, v.y), mn2), sc2, of2);
+          const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v.z, v.w), mn2), sc2, of2);
+          t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int e = tid; e < n4; e += kVThreads) {
         const float4 v = t4[e];
         const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v.x, v.y), mn2), sc2, of2);
         const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v.z, v.w), mn2), sc2, of2);
