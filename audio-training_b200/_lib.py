@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcacfe.so")
 SOURCES = ["cacfe.cu"]
-HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "k_frontend_stream.cuh", "k_frontend_v3.cuh", "k_pcen.cuh",
+HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "cacfe_async.cuh", "k_frontend_v3.cuh", "fft64x2_gen.cuh", "mel_jobs.h",
+           "k_melspec_tc.cuh", "k_sosfilt.cuh", "k_pcen.cuh",
            "k_compress.cuh", "k_melspec.cuh", os.path.join("..", "..", "include", "cacfe.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -71,6 +72,7 @@ PROTOTYPES = {
                            c_void_p, c_void_p]),
     "cacfe_compress": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p,
                                c_void_p]),
+    "cacfe_sosfilt": (c_int, [c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
     "cacfe_frontend_pcen": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "cacfe_hostpipe_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "cacfe_hostpipe_destroy": (None, [c_void_p]),

@@ -184,6 +184,16 @@ class Plan:
                                                  _stream(self.device)))
         return out
 
+    def sosfilt(self, sos, x):
+        """scipy.signal.sosfilt(sos, x) along the last axis (float64 recurrence, float32 result) on the device."""
+        x = self._check_in(x, "sosfilt")
+        sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64).reshape(-1, 6))
+        out = torch.empty_like(x)
+        n = x.shape[-1]
+        _lib.check(self._lib.cacfe_sosfilt(self._handle, sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), sos.shape[0],
+                                           _ptr(x), _ptr(out), x.numel() // n, n, _stream(self.device)))
+        return out
+
     def mel_from_spectrogram(self, spec):
         spec = self._check_in(spec, "mel_from_spectrogram")
         if spec.dim() != 3 or spec.shape[1] != self.n_bins:

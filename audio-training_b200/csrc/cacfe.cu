@@ -16,11 +16,11 @@
 #include "../../include/cacfe.h"
 #include "k_compress.cuh"
 #include "k_frontend.cuh"
-#include "k_frontend_stream.cuh"
 #include "k_frontend_v3.cuh"
 #include "k_melspec.cuh"
 #include "k_melspec_tc.cuh"
 #include "k_pcen.cuh"
+#include "k_sosfilt.cuh"
 
 namespace {
 
@@ -61,20 +61,19 @@ struct cacfe_plan {
   int* d_band_start = nullptr;
   int* d_band_ofs = nullptr;
   cacfe::K1Smem k1;
-  cacfe::SSmem ks;
   cacfe::VSmem kv;
   cacfe::MelJobs jobs;
   float4* d_mel_w = nullptr;
   float4* d_tw4 = nullptr;
+  float* d_win_full = nullptr;
+  int nq_v3 = 0;     // 64-bin column groups of the 4096-point grid the (strided) bank reaches
   // tcgen05 stored-spectrogram path (CACFE_MEL_TC_3XTF32)
   bool tc_ok = false;
   std::vector<cacfe::MelTcChunk> tc_chunks;
   float* d_tc_w = nullptr;
   cacfe::MelTcChunk* d_tc_chunks = nullptr;
   int* d_mel_desc = nullptr;
-  bool stream_ok = false;
   bool v3_ok = false;
-  int variant = 3;  // 3: persistent small-code kernel; 2: previous streaming kernel (CACFE_K1_VARIANT, experiments)
   bool force_generic = false;  // tests: run the non-streaming kernel on configurations that allow both
   bool frontend_ok = false;
   std::atomic<long long> launches{0};
@@ -265,13 +264,20 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
   if (p->k1.total > (size_t)prop.sharedMemPerBlockOptin) p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 0);
   p->frontend_ok = cfg->n_fft == cacfe::kFft && p->k1.total <= (size_t)prop.sharedMemPerBlockOptin;
-  // streaming (TMA) form: needs 16-byte aligned clips and no reflected samples
-  p->ks = cacfe::stream_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
-  if (p->ks.total > (size_t)prop.sharedMemPerBlockOptin) p->ks = cacfe::stream_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 0);
-  p->stream_ok = p->frontend_ok && p->ks.total <= (size_t)prop.sharedMemPerBlockOptin && cfg->n_samples % 4 == 0 &&
-                 cfg->framing != CACFE_FRAME_CENTER_REFLECT;
 
-  p->jobs = cacfe::build_mel_jobs(p->bank.data(), cfg->n_mels, p->n_bins, 32 * (p->nq <= 15 ? 15 : 33));
+  // persistent kernel: 4096-point transform; shorter n_fft = 4096 / r use bins r k of it (bank placed with stride r)
+  const bool fft_divides = cfg->n_fft >= 512 && cfg->n_fft <= cacfe::kFft && cacfe::kFft % cfg->n_fft == 0;
+  const int ratio = fft_divides ? cacfe::kFft / cfg->n_fft : 1;
+  std::vector<float> bank4096;
+  const float* bank_v3 = p->bank.data();
+  if (fft_divides && ratio > 1) {
+    bank4096.assign((size_t)cfg->n_mels * (cacfe::kFft / 2 + 1), 0.0f);
+    for (int m = 0; m < cfg->n_mels; ++m)
+      for (int k = 0; k < p->n_bins; ++k) bank4096[(size_t)m * (cacfe::kFft / 2 + 1) + (size_t)ratio * k] = p->bank[(size_t)m * p->n_bins + k];
+    bank_v3 = bank4096.data();
+  }
+  p->nq_v3 = (ratio * hi) / 64 + 1;
+  p->jobs = cacfe::build_mel_jobs(bank_v3, cfg->n_mels, cacfe::kFft / 2 + 1, 32 * (p->nq_v3 <= 15 ? 15 : 33));
   p->kv = cacfe::v3_smem_layout(cfg->hop, p->jobs.total_quads);
   bool reflect_fits = true;
   if (cfg->framing == CACFE_FRAME_CENTER_REFLECT)
@@ -282,10 +288,9 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
       if (p_max >= cfg->n_samples && 2LL * (cfg->n_samples - 1) - p_max < std::max(s_lo, 0LL)) reflect_fits = false;
       if (s_lo < 0 && -s_lo >= s_lo + p->kv.tile_len) reflect_fits = false;
     }
-  p->v3_ok = p->frontend_ok && p->jobs.ok && p->kv.total <= (size_t)prop.sharedMemPerBlockOptin &&
+  p->v3_ok = fft_divides && p->jobs.ok && p->kv.total <= (size_t)prop.sharedMemPerBlockOptin &&
              p->kv.tile_pad <= cacfe::kNormIters * cacfe::kVThreads * 4 &&
              cfg->n_samples % 4 == 0 && reflect_fits;
-  if (const char* v = std::getenv("CACFE_K1_VARIANT")) p->variant = std::atoi(v);
 
   // tables
   std::vector<float2> tw(4096);
@@ -302,6 +307,9 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
         tw4[(pr * 64 + n2) * 4 + h] = (float)std::cos(ang);
         tw4[(pr * 64 + n2) * 4 + 2 + h] = (float)std::sin(ang);
       }
+  std::vector<float> win_full(cacfe::kFft, 0.0f);   // periodic Hann of length n_fft (tf.signal.hann_window / scipy fftbins)
+  if (fft_divides)
+    for (int n = 0; n < cfg->n_fft; ++n) win_full[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)cfg->n_fft));
   std::vector<float> win(2049);
   for (int n = 0; n <= 2048; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / 4096.0));
 
@@ -317,19 +325,16 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess) e = upload((void**)&p->d_band_start, bfirst.data(), bfirst.size() * sizeof(int));
   if (e == cudaSuccess) e = upload((void**)&p->d_band_ofs, bofs.data(), bofs.size() * sizeof(int));
   if (e == cudaSuccess && p->frontend_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
+    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
   if (e == cudaSuccess && p->frontend_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k1.total);
-  if (e == cudaSuccess && p->stream_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
-  if (e == cudaSuccess && p->stream_ok)
-    e = cudaFuncSetAttribute(cacfe::stft_mel_stream_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ks.total);
+    e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
   if (e == cudaSuccess && p->tc_ok) e = upload((void**)&p->d_tc_w, tc_w.data(), tc_w.size() * sizeof(float));
   if (e == cudaSuccess && p->tc_ok)
     e = upload((void**)&p->d_tc_chunks, p->tc_chunks.data(), p->tc_chunks.size() * sizeof(cacfe::MelTcChunk));
   if (e == cudaSuccess && p->tc_ok)
     e = cudaFuncSetAttribute(cacfe::melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kTcSmemBytes);
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
+  if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_win_full, win_full.data(), win_full.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok) {
@@ -338,7 +343,9 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
                               (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM>,
                               (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC>};
     for (int q = 0; q < 4 && e == cudaSuccess; ++q)
-      e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->kv.total);
+      // the attribute belongs to the function, not to the plan: always the device maximum, so that a plan created later
+      // with a smaller layout cannot shrink it under an earlier plan
+      e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
   }
   if (e != cudaSuccess) {
     cacfe_plan_destroy(p);
@@ -360,6 +367,7 @@ void cacfe_plan_destroy(cacfe_plan* p) {
   cudaFree(p->d_tc_w);
   cudaFree(p->d_tc_chunks);
   cudaFree(p->d_tw4);
+  cudaFree(p->d_win_full);
   cudaFree(p->d_mel_desc);
   delete p;
 }
@@ -517,9 +525,9 @@ int cacfe_normalize(cacfe_plan* p, const float* in, float* out, long long rows, 
 
 static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, int layout, int channels, void* ws,
                            cudaStream_t st) {
-  if (!p->frontend_ok)
-    return fail(CACFE_EINVAL, "frontend: the fused kernel is built for n_fft=4096 (got %d) and needs %zu B of shared memory",
-                p->cfg.n_fft, p->k1.total);
+  if (!p->frontend_ok && !p->v3_ok)
+    return fail(CACFE_EINVAL, "frontend: n_fft=%d is not served by the fused kernels (4096; 512..2048 through the persistent "
+                "kernel, which needs n_samples %% 4 == 0 and a bank of at most 192 bands)", p->cfg.n_fft);
   cacfe::FrontendArgs a;
   int launches = 1;
   a.norm = nullptr;
@@ -561,13 +569,13 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     cudaEventRecord(ev0, st);
   }
   const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
-  const bool v3 = p->v3_ok && !p->force_generic && aligned && p->variant == 3 &&
+  const bool v3 = p->v3_ok && !p->force_generic && aligned &&
                   (reinterpret_cast<uintptr_t>(a.norm) & 15) == 0;  // the kernel bulk-copies 16-byte pairs of it
-  const bool stream = p->stream_ok && !p->force_generic && aligned;
   if (v3) {
     cacfe::MelArgs mj;
     mj.w = p->d_mel_w;
     mj.tw4 = p->d_tw4;
+    mj.win = p->d_win_full;
     mj.desc = p->d_mel_desc;
     for (int sgm = 0; sgm < cacfe::kMelMaxSeg; ++sgm) mj.nq[sgm] = p->jobs.nq[sgm];
     mj.split_seg = p->jobs.split_seg;
@@ -577,22 +585,18 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     const long long tiles = (long long)B * a.tiles_per_clip;
     const unsigned ctas = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);  // one persistent CTA per SM
     const bool btm = layout == CACFE_LAYOUT_BTM;
-    if (p->nq <= 15 && btm)
+    if (p->nq_v3 <= 15 && btm)
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
-    else if (p->nq <= 15)
+    else if (p->nq_v3 <= 15)
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (btm)
       cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else
       cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
-  } else if (stream) {
-    a.bw_in_smem = p->ks.bw_in_smem;
-    const unsigned ctas = (unsigned)(grid < p->sm_count ? grid : p->sm_count);  // one persistent CTA per SM
-    if (p->nq <= 15)
-      cacfe::stft_mel_stream_kernel<15><<<ctas, cacfe::kSThreads, p->ks.total, st>>>(a, (int)grid);
-    else
-      cacfe::stft_mel_stream_kernel<33><<<ctas, cacfe::kSThreads, p->ks.total, st>>>(a, (int)grid);
   } else {
+    if (!p->frontend_ok)
+      return fail(CACFE_EINVAL, "frontend: n_fft=%d needs the persistent kernel (16-byte aligned input, not forced generic)",
+                  p->cfg.n_fft);
     a.bw_in_smem = p->k1.bw_in_smem;
     if (p->nq <= 15)
       cacfe::stft_mel_kernel<15><<<(unsigned)grid, cacfe::kK1Threads, p->k1.total, st>>>(a);
@@ -756,6 +760,28 @@ int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float*
       break;
   }
   return check_launch(p, "compress", launches);
+}
+
+int cacfe_sosfilt(cacfe_plan* p, const double* sos_host, int n_sections, const float* in, float* out, long long rows,
+                  long long n, void* stream) {
+  if (!p || !sos_host || !in || !out) return fail(CACFE_EINVAL, "sosfilt: null argument");
+  if (n_sections < 1 || n_sections > cacfe::kSosMaxSections)
+    return fail(CACFE_EINVAL, "sosfilt: 1..%d sections supported (got %d)", cacfe::kSosMaxSections, n_sections);
+  if (rows < 1 || n < 1) return fail(CACFE_ESHAPE, "sosfilt: bad shape");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cacfe::SosArgs a{};
+  a.in = in;
+  a.out = out;
+  a.rows = rows;
+  a.n = n;
+  a.n_sections = n_sections;
+  for (int s = 0; s < n_sections; ++s) {
+    const double a0 = sos_host[6 * s + 3];
+    if (a0 == 0.0) return fail(CACFE_EINVAL, "sosfilt: a0 == 0 in section %d", s);
+    for (int c = 0; c < 6; ++c) a.sos[s][c] = sos_host[6 * s + c] / a0;  // scipy normalises by a0 as well
+  }
+  cacfe::sosfilt_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(a);
+  return check_launch(p, "sosfilt");
 }
 
 int cacfe_frontend_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* raw, float* out, int B, void* ws,

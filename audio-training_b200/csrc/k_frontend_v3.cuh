@@ -16,18 +16,24 @@
 //     instruction-cache lines;
 //   * the mel projection is balanced across the 64 threads of a group (serpentine band order, the short last
 //     round split across lane pairs) -- the old order left one warp with 48 taps and the other with 22.
+// Shorter transforms ride the same kernel: a frame of n_fft = 4096 / r samples, zero padded to 4096, has its DFT at every
+// r-th bin of the 4096-point one, so the plan zero-pads the window and places the filterbank weights on bins r k
+// (tf.signal.stft(1024 | 2048, ...) of raw_to_mel_rgb / raw_to_mel_dual, tfdataset.py:1818-2004).  r x the FFT work of a
+// dedicated kernel; those variants are not on the benchmarked path.
 // Sample tiles still arrive by TMA bulk copy (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a 2-deep ring.
 #pragma once
 #include "cacfe_common.cuh"
 #include "frontend_core.cuh"
 #include "k_frontend.cuh"
-#include "k_frontend_stream.cuh"  // mbarrier / bulk-copy wrappers
+#include "cacfe_async.cuh"  // mbarrier / bulk-copy wrappers
 #include "fft64x2_gen.cuh"
 #include "mel_jobs.h"
 
 namespace cacfe {
 
 constexpr int kVGroups = 6;
+constexpr int kHalfStride = 68;                    // floats per half-exchange row: 272 B = 2*128 + 16
+constexpr int kHalfFloats = 64 * kHalfStride;      // 17408 B per group
 constexpr int kVThreads = kVGroups * 64;
 constexpr int kVTileFrames = 2 * kVGroups;
 constexpr int kNormIters = 6;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
@@ -43,7 +49,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
   s.tile_len = kFft + hop * (kVTileFrames - 1);
   s.tile_pad = (s.tile_len + 3 + 4) & ~3;          // room for the copy length rounded up to 16 B
   size_t o = sizeof(float2) * 4096;
-  s.off_win = o;    o += sizeof(float) * 2052;
+  s.off_win = o;    o += sizeof(float) * kFft;      // full window: Hann(n_fft) zero padded to 4096 (n_fft < 4096)
   s.off_tile = o;   o += sizeof(float) * s.tile_pad * 2;
   s.off_exch = o;   o += sizeof(float) * kHalfFloats * kVGroups;
   s.off_melw = o;   o += sizeof(float4) * 64 * (mel_quads > 0 ? mel_quads : 1);
@@ -56,6 +62,7 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
 // Mel job tables of the plan (mel_jobs.h), device copies.
 struct MelArgs {
   const float4* tw4;  // [32][64] stage twiddles, packed per output pair: (cos k, cos k+1, sin k, sin k+1)
+  const float* win;   // [4096] periodic Hann of length n_fft, zero beyond n_fft
   const float4* w;    // [total_quads][64]
   const int* desc;    // [kMelMaxSeg][64]
   int nq[kMelMaxSeg];
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   // ---- tables, once per CTA (L2 resident) ------------------------------------------------------------------
   {
     for (int i = tid; i < 2048; i += kVThreads) s_tw4[i] = mj.tw4[i];
-    for (int i = tid; i < 2049; i += kVThreads) s_win[i] = a.win[i];
+    for (int i = tid; i < kFft; i += kVThreads) s_win[i] = mj.win[i];
     for (int i = tid; i < 64 * mj.total_quads; i += kVThreads) s_melw[i] = mj.w[i];
     for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
   }
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
 #pragma unroll
         for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
           const int n = 64 * q + t64;
-          const cacfe_f2 wv = cacfe_pk(s_win[q < 32 ? n : kFft - n], s_win[q + 1 < 32 ? n + 64 : kFft - n - 64]);
+          const cacfe_f2 wv = cacfe_pk(s_win[n], s_win[n + 64]);
           const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv);
           const cacfe_f2 xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
           re[q] = cacfe_lo(xa);

@@ -22,7 +22,7 @@
 // HBM bound: 930 rows x 513 x 4 B in, 160 x 513 x 4 B out per clip.
 #pragma once
 #include "cacfe_common.cuh"
-#include "k_frontend_stream.cuh"  // mbarrier / bulk-copy wrappers
+#include "cacfe_async.cuh"  // mbarrier / bulk-copy wrappers
 
 namespace cacfe {
 

@@ -95,14 +95,74 @@ def raw_to_mel(x, y, features=False):
     return _repack(restore(out[0] if single else out), packed), y
 
 
+# tfdataset.py:50-54: the two 1024-point banks of the multi-resolution variants are fixed at import time (160 bands)
+MEL_WEIGHTS_2 = _cached_bank(SR, 160, 100.0, 3000.0, 1024, float(BREAK_FREQ))
+MEL_WEIGHTS_3 = _cached_bank(SR, 160, 500.0, 11000.0, 1024, float(BREAK_FREQ))
+
+
+def _stft_mel(t, bank, n_fft, hop, framing, power):
+    """[B, N] -> [B, n_mels, T] through the fused kernel (n_fft < 4096 rides the 4096-point transform, k_frontend_v3.cuh)."""
+    cfg = rt.FrontendConfig(sr=SR, n_samples=int(t.shape[-1]), n_fft=int(n_fft), hop=int(hop), framing=framing,
+                            n_mels=int(bank.shape[0]), fmin=0.0, fmax=0.0, break_freq=float(BREAK_FREQ), power=power,
+                            channels=1, out_layout="bmtc")
+    return rt.get_plan(cfg, t.device.index, bank).frontend(t)[..., 0]
+
+
 def raw_to_mel_rgb(x, y):
-    """tfdataset.py:1937-2004 needs 1024-point STFTs (a15): not built -- only the 4096/281 path is."""
-    raise NotImplementedError("raw_to_mel_rgb uses 1024-point STFTs; this build fuses the 4096-point path only")
+    """tfdataset.py:1937-2004: pad_end power spectrograms at 4096 (MEL_WEIGHTS), 1024 (MEL_WEIGHTS_2) and 1024
+    (MEL_WEIGHTS_3) points, hop 281, as three different channels.  [B, N] -> [B, n_mels, T, 3]."""
+    raw, packed = _unpack(x)
+    t, restore = rt.to_device(raw)
+    single = t.dim() == 1
+    if single:
+        t = t.unsqueeze(0)
+    chans = [_stft_mel(t, MEL_WEIGHTS, 4096, HOP_LENGTH, "tf_pad_end", 2),
+             _stft_mel(t, MEL_WEIGHTS_2, 1024, HOP_LENGTH, "tf_pad_end", 2),
+             _stft_mel(t, MEL_WEIGHTS_3, 1024, HOP_LENGTH, "tf_pad_end", 2)]
+    out = torch.stack(chans, dim=3)
+    return _repack(restore(out[0] if single else out), packed), y
+
+
+def butter_function(x, lowcut, highcut, order=2):
+    """tfdataset.py:2062-2077 (+ butter_bandpass :1768-1786): Butterworth low / band / high-pass as second-order sections,
+    causal sosfilt along the last axis.  The reference leaves the graph for scipy on the CPU (tf.numpy_function); here the
+    filter design is scipy on the host (six numbers per section) and the recurrence runs on the device in float64."""
+    from scipy.signal import butter
+    t, restore = rt.to_device(x)
+    if lowcut <= 0 and highcut <= 0:
+        return restore(t)
+    nyq = 0.5 * SR
+    btype, freqs = "lowpass", []
+    if lowcut > 0:
+        btype = "bandpass"
+        freqs.append(lowcut / nyq)
+    if highcut > 0 and highcut / nyq < 1:
+        freqs.append(highcut / nyq)
+    else:
+        btype = "highpass"
+    if not freqs:
+        return restore(t)
+    sos = butter(order, freqs, analog=False, btype=btype, output="sos")
+    return restore(_any_plan(t.device.index).sosfilt(sos, t))
 
 
 def raw_to_mel_dual(x, y):
-    """tfdataset.py:1818-1866 needs 2048/1024-point STFTs and a Butterworth pre-filter (a15): not built."""
-    raise NotImplementedError("raw_to_mel_dual uses 2048/1024-point STFTs; this build fuses the 4096-point path only")
+    """tfdataset.py:1818-1866: low-pass 3 kHz, then MAGNITUDE mel of a 2048/278 STFT (MEL_WEIGHTS, set with
+    configure(n_fft=2048, ...)) and of a 1024/280 STFT (MEL_WEIGHTS_2), both without pad_end (511 frames) and both of the
+    SAME filtered signal (Q15).  -> ((B, n_mels, 511, 1), (B, 160, 511, 1)), y."""
+    t, restore = rt.to_device(x)
+    single = t.dim() == 1
+    if single:
+        t = t.unsqueeze(0)
+    raw = butter_function(t, 0, 3000)
+    if MEL_WEIGHTS.shape[1] != 1025:
+        raise ValueError("raw_to_mel_dual: MEL_WEIGHTS must be a 2048-point bank -- call configure(n_fft=2048, ...) as "
+                         "get_dataset does (tfdataset.py:441-452)")
+    a = _stft_mel(raw, MEL_WEIGHTS, 2048, 278, "no_pad", 1).unsqueeze(3)
+    b = _stft_mel(raw, MEL_WEIGHTS_2, 1024, 280, "no_pad", 1).unsqueeze(3)
+    if single:
+        a, b = a[0], b[0]
+    return (restore(a), restore(b)), y
 
 
 def mel_from_spectrogram(spectogram, model_name="", pcen=True):

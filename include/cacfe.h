@@ -59,7 +59,7 @@ typedef enum cacfe_mel_impl {
 typedef struct cacfe_config {
   int32_t sr;          /* 48000 */
   int32_t n_samples;   /* samples per clip, 144000 */
-  int32_t n_fft;       /* frame length == FFT length; 4096 */
+  int32_t n_fft;       /* frame length == FFT length; 4096 (fused kernels); 512, 1024, 2048 ride the 4096-point kernel */
   int32_t hop;         /* 281 */
   int32_t framing;     /* cacfe_framing */
   int32_t n_mels;      /* 160 */
@@ -159,6 +159,11 @@ int cacfe_pcen(cacfe_plan* plan, const cacfe_pcen_params* params, const float* i
 /* ---- a12-a14: point-wise compression with a tensor- (entries = 1) or clip-wide (entries = B) statistic. */
 int cacfe_compress(cacfe_plan* plan, int mode, float param, const float* in_dev, float* out_dev, long long entries,
                    long long per_entry, void* workspace_dev, void* stream);
+
+/* ---- a15: butter_function / butter_bandpass_filter tfdataset.py:2062-2077 (scipy.signal.sosfilt along the last axis,
+ * float64 recurrence, float32 result).  sos_host: host [n_sections][6] as scipy.signal.butter(..., output="sos") returns. */
+int cacfe_sosfilt(cacfe_plan* plan, const double* sos_host, int n_sections, const float* in_dev, float* out_dev,
+                  long long rows, long long n, void* stream);
 
 /* ---- raw clips -> mel [B][T][n_mels] -> PCEN, device pointers.  normalize + raw_to_mel + PCEN in one call;
  * the mel intermediate lives in the workspace. */

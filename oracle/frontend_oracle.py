@@ -214,6 +214,58 @@ def raw_to_mel(x, weights=None, n_fft=N_FFT, hop=HOP, pad_end=True, channels=3, 
     return img[0] if single else img
 
 
+# --------------------------------------------------------------------------------------
+# a15  multi-resolution variants                    tfdataset.py:1818-1866, 1937-2004
+# --------------------------------------------------------------------------------------
+def butter_sos(lowcut, highcut, fs=48000, order=2):
+    """butter_bandpass (tfdataset.py:1768-1786): low-pass when lowcut <= 0, high-pass when highcut is at or
+    above Nyquist, band-pass otherwise; second-order sections.  None when there is nothing to filter."""
+    from scipy.signal import butter
+    nyq = 0.5 * fs
+    btype, freqs = "lowpass", []
+    if lowcut > 0:
+        btype = "bandpass"
+        freqs.append(lowcut / nyq)
+    if highcut > 0 and highcut / nyq < 1:
+        freqs.append(highcut / nyq)
+    else:
+        btype = "highpass"
+    if not freqs:
+        return None
+    return butter(order, freqs, analog=False, btype=btype, output="sos")
+
+
+def butter_bandpass_filter(data, lowcut, highcut, fs=48000, order=2):
+    """tfdataset.py:2070-2077: causal sosfilt along the last axis (scipy works in f64), result cast to f32."""
+    from scipy.signal import sosfilt
+    if lowcut <= 0 and highcut <= 0:
+        return data
+    sos = butter_sos(lowcut, highcut, fs, order)
+    if sos is None:
+        return data
+    return np.float32(sosfilt(sos, data))
+
+
+def raw_to_mel_rgb(x, w_4096, w_1024_a, w_1024_b, hop=HOP, dtype=np.float64):
+    """tfdataset.py:1937-2004: three pad_end power spectrograms -- 4096-point with MEL_WEIGHTS, 1024-point with
+    MEL_WEIGHTS_2 and again 1024-point with MEL_WEIGHTS_3 -- concatenated as three DIFFERENT channels.
+    -> [B, n_mels, T, 3]."""
+    c0 = raw_to_mel(x, w_4096, 4096, hop, True, 0, 2, dtype)
+    c1 = raw_to_mel(x, w_1024_a, 1024, hop, True, 0, 2, dtype)
+    c2 = raw_to_mel(x, w_1024_b, 1024, hop, True, 0, 2, dtype)
+    return np.stack([c0, c1, c2], axis=-1)
+
+
+def raw_to_mel_dual(x, w_2048, w_1024, dtype=np.float64):
+    """tfdataset.py:1818-1866: low-pass 3 kHz (order 2, causal), then MAGNITUDE (not power) mel of a 2048/278 STFT
+    without pad_end (511 frames); the second image is a 1024/280 STFT of the SAME, already filtered signal (Q15:
+    the 500-15000 Hz band-pass result `raw2` is computed and never used).  -> ([B, M1, 511, 1], [B, M2, 511, 1])."""
+    raw = butter_bandpass_filter(np.asarray(x, dtype=np.float32), 0, 3000)
+    a = raw_to_mel(raw, w_2048, 2048, 278, False, 0, 1, dtype)[..., None]
+    b = raw_to_mel(raw, w_1024, 1024, 280, False, 0, 1, dtype)[..., None]
+    return a, b
+
+
 def mel_spec(stft, sr, n_fft, hop_length, n_mels, fmin, fmax, break_freq=1750, power=2,
              dtype=np.float64):
     """custommel.py:57-61  |stft|**power then filterbank . magnitude (Q8: bank rebuilt per call,

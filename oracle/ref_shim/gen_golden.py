@@ -203,6 +203,24 @@ def main():
         pcen_serial_key=np.asarray([tfpcen.PCEN._serial_key, ns2["MagTransform"]._serial_key]),
     )
 
+    # ---------------- a15: raw_to_mel_rgb / raw_to_mel_dual (tfdataset.py:1818-1866, 1937-2004) over the shim ----------
+    import scipy.signal as _ss
+    ns3 = {"tf": tf, "logging": __import__("logging"), "np": np, "butter": _ss.butter, "sosfilt": _ss.sosfilt}
+    cut_out(os.path.join(REF, "tfdataset.py"),
+            ["raw_to_mel_rgb", "raw_to_mel_dual", "butter_function", "butter_bandpass_filter", "butter_bandpass"], ns3)
+    ns3.update(MEL_WEIGHTS=W, MEL_WEIGHTS_2=banks["nfft1024_lo"], MEL_WEIGHTS_3=banks["nfft1024_hi"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        rgb, _ = ns3["raw_to_mel_rgb"](clips_norm[:1], None)                      # [1,160,513,3], three different channels
+    assert rgb.shape == (1, 160, 513, 3)
+    ns3.update(MEL_WEIGHTS=banks["mels96_2048"])                                   # get_dataset(n_fft=2048, n_mels=96)
+    with contextlib.redirect_stdout(io.StringIO()):
+        (dual_1, dual_2), _ = ns3["raw_to_mel_dual"](clips_norm[:1], None)        # [1,96,511,1], [1,160,511,1]
+    assert dual_1.shape == (1, 96, 511, 1) and dual_2.shape == (1, 160, 511, 1)
+    lowpassed = ns3["butter_bandpass_filter"](clips_norm[:1], 0, 3000, 48000, 2)   # the filter alone
+    np.savez_compressed(os.path.join(OUT, "variants.npz"), rgb=rgb.astype(np.float32), dual_1=dual_1.astype(np.float32),
+                        dual_2=dual_2.astype(np.float32), lowpassed_head=np.asarray(lowpassed)[0, :4096].astype(np.float32),
+                        lowpassed_tail=np.asarray(lowpassed)[0, -4096:].astype(np.float32))
+
     # ---------------- a8: load_samples integer arithmetic (real code, recording the slices) --
     cases = []
     sr = 48000

@@ -149,6 +149,11 @@ def squeeze(x, axis=None, name=None):
     return np.squeeze(x, axis=axis)
 
 
+def numpy_function(func, inp, Tout, name=None):
+    """tf.numpy_function: call a Python function on the (numpy) values and cast the result to Tout."""
+    return np.asarray(func(*[np.asarray(v) if isinstance(v, np.ndarray) else v for v in inp]), dtype=Tout)
+
+
 def function(fn=None, **_kw):  # @tf.function -> eager
     if fn is None:
         return lambda f: f

@@ -4,9 +4,13 @@ oracle and the committed golden vectors.
 Tolerance (north star): |ours - truth| <= 1e-4 * |truth| + 1e-5, truth = float64 oracle.  Integer / index work
 (frame counts, shapes, window tables) and the f32 normalisation / EMA are compared bit for bit.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
+
+from conftest import GOLDEN
 
 import audio_training_b200 as atb
 from audio_training_b200 import _runtime as rt
@@ -230,6 +234,36 @@ def test_path_c_tensor_core(oracle, xn, bank, power, layout, channels):
         assert torch.equal(tc[..., 0], tc[..., 2])
 
 
+# ------------------------------------------------------------------------------------------------ a15 variants
+def test_multi_resolution_variants(oracle, golden_banks, xn):
+    """raw_to_mel_rgb / raw_to_mel_dual (tfdataset.py:1818-2004): 1024- and 2048-point STFTs through the 4096-point kernel
+    (zero-padded window, bank on every r-th bin), the Butterworth pre-filter on the device."""
+    g = np.load(os.path.join(GOLDEN, "variants.npz"))
+    x = xn[:1]
+    wlo, whi = golden_banks["nfft1024_lo"], golden_banks["nfft1024_hi"]
+    assert np.array_equal(td.MEL_WEIGHTS_2, wlo) and np.array_equal(td.MEL_WEIGHTS_3, whi)
+    td.configure(n_mels=160, fmin=100, fmax=11000, n_fft=4096, break_freq=1000)
+    rgb, y = td.raw_to_mel_rgb(x, "label")
+    assert y == "label" and rgb.shape == (1, 160, 513, 3)
+    check(oracle, rgb, oracle.raw_to_mel_rgb(x, golden_banks["train_fmin100"], wlo, whi), what="rgb vs f64 oracle")
+    check(oracle, rgb, g["rgb"], 2.0, what="rgb vs reference-code golden")
+    low = td.butter_function(x, 0, 3000)
+    assert np.allclose(low[0, :4096], g["lowpassed_head"], rtol=0, atol=2e-7)
+    assert np.allclose(low[0, -4096:], g["lowpassed_tail"], rtol=0, atol=2e-7)
+    try:
+        td.configure(n_mels=96, n_fft=2048)
+        assert np.array_equal(td.MEL_WEIGHTS, golden_banks["mels96_2048"])
+        (d1, d2), _ = td.raw_to_mel_dual(x, None)
+    finally:
+        td.configure(n_mels=160, fmin=100, fmax=11000, n_fft=4096, break_freq=1000)
+    assert d1.shape == (1, 96, 511, 1) and d2.shape == (1, 160, 511, 1)
+    w1, w2 = oracle.raw_to_mel_dual(x, golden_banks["mels96_2048"], wlo)
+    check(oracle, d1, w1, what="dual (2048/278) vs f64 oracle")
+    check(oracle, d2, w2, what="dual (1024/280) vs f64 oracle")
+    check(oracle, d1, g["dual_1"], 2.0, what="dual 1 vs reference-code golden")
+    check(oracle, d2, g["dual_2"], 2.0, what="dual 2 vs reference-code golden")
+
+
 # ------------------------------------------------------------------------------------------------ PCEN
 def test_ema_bit_exact(oracle, golden):
     x = np.swapaxes(golden["path_a"], 1, 2).copy()
@@ -313,11 +347,11 @@ def test_errors():
         plan.frontend(torch.zeros(2, 1000, device="cuda"))
     with pytest.raises(TypeError):
         plan.frontend(torch.zeros(2, 144000, device="cuda", dtype=torch.float64))
-    with pytest.raises(atb.CacfeError):
-        rt.Plan(rt.FrontendConfig(n_fft=2048, n_mels=96), 0).frontend(torch.zeros(1, 144000, device="cuda"))
+    with pytest.raises(atb.CacfeError):   # 4096 % n_fft != 0: no fused kernel serves it
+        rt.Plan(rt.FrontendConfig(n_fft=3000, n_mels=96), 0).frontend(torch.zeros(1, 144000, device="cuda"))
     with pytest.raises(atb.CacfeError):
         rt.Plan(rt.FrontendConfig(power=3), 0)
-    with pytest.raises(NotImplementedError):
-        td.raw_to_mel_dual(None, None)
+    with pytest.raises(ValueError):       # raw_to_mel_dual needs the 2048-point bank get_dataset(n_fft=2048) sets
+        td.raw_to_mel_dual(torch.zeros(1, 144000, device="cuda"), None)
     assert plan.bin_range() == (9, 938)
     assert plan.launch_count() >= 0

@@ -202,3 +202,28 @@ def test_generator_is_index_keyed(oracle):
     b = oracle.synth_clips([9], n=4096)
     assert np.array_equal(a[1], b[0])
     assert a.dtype == np.float32 and np.abs(a).max() < 2.0
+
+
+def test_multi_resolution_variants_match_reference_code(oracle, golden_banks):
+    """a15: raw_to_mel_rgb / raw_to_mel_dual restated in the oracle against the reference's own source executed over the
+    tf shim (tests/golden/variants.npz, oracle/ref_shim/gen_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "variants.npz"))
+    x = oracle.normalize(oracle.synth_clips([0]), np.float32)
+    w4096, wlo, whi = golden_banks["train_fmin100"], golden_banks["nfft1024_lo"], golden_banks["nfft1024_hi"]
+    rgb = oracle.raw_to_mel_rgb(x, w4096, wlo, whi, dtype=np.float32)
+    assert rgb.shape == g["rgb"].shape == (1, 160, 513, 3)
+    ok, worst = oracle.within_tolerance(rgb, g["rgb"])
+    assert ok, worst
+    assert not np.allclose(g["rgb"][..., 1], g["rgb"][..., 2])            # three different channels
+    low = oracle.butter_bandpass_filter(x, 0, 3000)
+    assert np.array_equal(low[0, :4096], g["lowpassed_head"]) and np.array_equal(low[0, -4096:], g["lowpassed_tail"])
+    d1, d2 = oracle.raw_to_mel_dual(x, golden_banks["mels96_2048"], wlo, dtype=np.float32)
+    assert d1.shape == g["dual_1"].shape == (1, 96, 511, 1) and d2.shape == g["dual_2"].shape == (1, 160, 511, 1)
+    for got, want in ((d1, g["dual_1"]), (d2, g["dual_2"])):
+        ok, worst = oracle.within_tolerance(got, want)
+        assert ok, worst
+    f64 = oracle.raw_to_mel_rgb(x, w4096, wlo, whi)                          # the f64 ground truth sits inside the budget too
+    ok, worst = oracle.within_tolerance(g["rgb"], f64)
+    assert ok, worst
