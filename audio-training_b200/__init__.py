@@ -6,7 +6,7 @@ module names: custommel, tfdataset, predict_utils, tfpcen, badwinner2.
 from . import _lib  # noqa: F401
 from ._lib import CacfeError, build  # noqa: F401
 from ._runtime import FrontendConfig, HostPipe, Plan, clear_plans, get_plan, pcen_params  # noqa: F401
-from . import badwinner2, custommel, distributed, predict_utils, tfdataset, tfpcen  # noqa: F401
+from . import audiodataset, badwinner2, custommel, distributed, predict_utils, tfdataset, tfpcen  # noqa: F401
 from .badwinner2 import MagTransform  # noqa: F401
 from .custommel import hz_to_mel, mel_f, mel_frequencies, mel_spec  # noqa: F401
 from .predict_utils import get_spect, load_samples, normalize_data  # noqa: F401

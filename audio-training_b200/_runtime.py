@@ -184,6 +184,18 @@ class Plan:
                                                  _stream(self.device)))
         return out
 
+    def stft(self, raw):
+        """raw [B, n_samples] -> |X| (power 1) or |X|^2 spectrogram [B, n_fft/2+1, T] in the plan's framing
+        (audiodataset.py:1301-1303: the stored `audio/spectogram` field; the input of mel_from_spectrogram)."""
+        raw = self._check_in(raw, "stft")
+        if raw.dim() != 2 or raw.shape[1] != self.config.n_samples:
+            raise ValueError(f"stft: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
+        B = raw.shape[0]
+        out = torch.empty((B, self.n_bins, self.n_frames), dtype=torch.float32, device=raw.device)
+        ws = self.workspace_for(B)
+        _lib.check(self._lib.cacfe_stft(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
+        return out
+
     def sosfilt(self, sos, x):
         """scipy.signal.sosfilt(sos, x) along the last axis (float64 recurrence, float32 result) on the device."""
         x = self._check_in(x, "sosfilt")

@@ -338,11 +338,12 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok) {
-    const void* kernels[4] = {(const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM>,
+    const void* kernels[5] = {(const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC>,
+                              (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM>,
                               (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC>,
                               (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM>,
                               (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC>};
-    for (int q = 0; q < 4 && e == cudaSuccess; ++q)
+    for (int q = 0; q < 5 && e == cudaSuccess; ++q)
       // the attribute belongs to the function, not to the plan: always the device maximum, so that a plan created later
       // with a smaller layout cannot shrink it under an earlier plan
       e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -585,7 +586,11 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     const long long tiles = (long long)B * a.tiles_per_clip;
     const unsigned ctas = (unsigned)(tiles < p->sm_count ? tiles : p->sm_count);  // one persistent CTA per SM
     const bool btm = layout == CACFE_LAYOUT_BTM;
-    if (p->nq_v3 <= 15 && btm)
+    mj.spec_ratio = cacfe::kFft / p->cfg.n_fft;
+    mj.spec_bins = p->n_bins;
+    if (layout == cacfe::LAYOUT_SPEC)
+      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    else if (p->nq_v3 <= 15 && btm)
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (p->nq_v3 <= 15)
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
@@ -594,6 +599,8 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     else
       cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
   } else {
+    if (layout == cacfe::LAYOUT_SPEC)
+      return fail(CACFE_EINVAL, "stft: the spectrogram output needs the persistent kernel (16-byte aligned input, n_samples %% 4 == 0)");
     if (!p->frontend_ok)
       return fail(CACFE_EINVAL, "frontend: n_fft=%d needs the persistent kernel (16-byte aligned input, not forced generic)",
                   p->cfg.n_fft);
@@ -618,6 +625,14 @@ int cacfe_frontend(cacfe_plan* p, const float* raw, float* feat, int B, void* ws
     return fail(CACFE_EALIGN, "frontend: buffers must be 4-byte aligned");
   CUDA_TRY(cudaSetDevice(p->device));
   return launch_frontend(p, raw, feat, B, p->cfg.out_layout, p->cfg.channels, ws, (cudaStream_t)stream);
+}
+
+int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, void* stream) {
+  if (!p || !raw || !spec) return fail(CACFE_EINVAL, "stft: null argument");
+  if (B < 1) return fail(CACFE_ESHAPE, "stft: B=%d", B);
+  if (p->cfg.normalize && !ws) return fail(CACFE_EINVAL, "stft: workspace required when normalize is set");
+  CUDA_TRY(cudaSetDevice(p->device));
+  return launch_frontend(p, raw, spec, B, cacfe::LAYOUT_SPEC, 1, ws, (cudaStream_t)stream);
 }
 
 int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, int B, int T, void* stream) {

@@ -67,6 +67,7 @@ struct MelArgs {
   const int* desc;    // [kMelMaxSeg][64]
   int nq[kMelMaxSeg];
   int split_seg, total_quads;
+  int spec_ratio, spec_bins;   // LAYOUT_SPEC: 4096 / n_fft and n_fft / 2 + 1
 };
 
 template <int NQ, int LAYOUT>
@@ -308,6 +309,55 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
 
+    if (LAYOUT == LAYOUT_SPEC) {
+      // ---- spectrogram output (audiodataset.load_data, audiodataset.py:1302-1303): |X| (power 1) or |X|^2 of every bin
+      // of an n_fft-point transform to out[b][k][t]; bins of the 4096-point grid that are not multiples of `ratio`
+      // belong to no bin of the shorter transform.  Rows are 8 bytes per pair here; the six groups of the CTA write the
+      // other 40 bytes of the same 48-byte run within the trip, so the sectors are merged in L2.
+      const bool row0 = j == 0;
+      const int ratio = mj.spec_ratio, n_out = mj.spec_bins;
+      float* obase = a.out + (size_t)b_cur * n_out * a.n_frames + ta;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float sr = __shfl_sync(kFullMask, re[63 - (q & 31)], plane);
+        const float si = __shfl_sync(kFullMask, im[63 - (q & 31)], plane);
+        if (q < 32) {
+          const float pr = row0 ? re[(64 - q) & 63] : sr;
+          const float pi = row0 ? im[(64 - q) & 63] : si;
+          const float zr = re[q], zi = im[q];
+          const float ar = zr + pr, ai = zi - pi, br = zr - pr, bi = zi + pi;
+          float va = fmaf(ar, ar, ai * ai), vb = fmaf(br, br, bi * bi);   // 4 |XA|^2, 4 |XB|^2
+          if (a.power == 1) {
+            va = 0.5f * sqrtf(va);
+            vb = 0.5f * sqrtf(vb);
+          } else {
+            va *= 0.25f;
+            vb *= 0.25f;
+          }
+          const int k = j + 64 * q;
+          if (k % ratio == 0) {
+            float* o = obase + (size_t)(k / ratio) * a.n_frames;
+            o[0] = va;
+            if (store_b) o[1] = vb;
+          }
+        } else if (row0) {
+          // Nyquist bin k = 2048 = row 0, q = 32: Z[2048] pairs with itself
+          const float zr = re[32], zi = im[32];
+          float va = 4.0f * zr * zr, vb = 4.0f * zi * zi;
+          if (a.power == 1) {
+            va = 0.5f * sqrtf(va);
+            vb = 0.5f * sqrtf(vb);
+          } else {
+            va *= 0.25f;
+            vb *= 0.25f;
+          }
+          float* o = obase + (size_t)(2048 / ratio) * a.n_frames;
+          o[0] = va;
+          if (store_b) o[1] = vb;
+        }
+      }
+      continue;
+    }
     // ---- split the two frames, power: bin k = j + 64 q goes to pbuf[k] as (4 |XA|^2, 4 |XB|^2) -------------------------
     // (the 1/4 of  XA = (Z[k] + conj Z[N-k]) / 2  is folded into the mel weights, mel_jobs.h)
     {

@@ -144,6 +144,11 @@ int cacfe_normalize(cacfe_plan* plan, const float* in_dev, float* out_dev, long 
  * feat_dev [B][n_mels][T][channels] or [B][T][n_mels]. */
 int cacfe_frontend(cacfe_plan* plan, const float* raw_dev, float* feat_dev, int B, void* workspace_dev, void* stream);
 
+/* ---- next row 1: the stored `audio/spectogram` field.  np.abs(librosa.stft(normed, n_fft, hop)) of
+ * audiodataset.load_data (audiodataset.py:1301-1303) with framing CENTER_*, power 1, normalize 1; any framing / power
+ * of the plan otherwise.  raw_dev [B][n_samples] -> spec_dev [B][n_fft/2+1][T] (t contiguous, what path C reads). */
+int cacfe_stft(cacfe_plan* plan, const float* raw_dev, float* spec_dev, int B, void* workspace_dev, void* stream);
+
 /* ---- a9: stored spectrogram -> mel.  tfdataset.py:1082-1099.  spec_dev [B][n_fft/2+1][T]. */
 int cacfe_mel_from_spectrogram(cacfe_plan* plan, const float* spec_dev, float* feat_dev, int B, int T, void* stream);
 

@@ -234,6 +234,32 @@ def test_path_c_tensor_core(oracle, xn, bank, power, layout, channels):
         assert torch.equal(tc[..., 0], tc[..., 2])
 
 
+# ------------------------------------------------------------------------------------------------ stored spectrogram
+def test_stored_spectrogram_producer(oracle, clips, xn, bank):
+    """cacfe_stft: the `audio/spectogram` field (audiodataset.py:1301-1303) = |librosa.stft(normalize_data(x))|, and the
+    loop it closes: mel_from_spectrogram(spectrogram(x)) is get_spect(normalize_data(x), power=1)."""
+    from audio_training_b200 import audiodataset as ad
+    got = ad.spectrogram(clips)                                           # normalises on the device
+    assert got.shape == (2, 2049, 513) and got.dtype == np.float32
+    for i in range(2):
+        want = np.abs(oracle.stft_librosa(xn[i]))                          # f64
+        err = np.abs(got[i] - want)
+        # an FP32 FFT is accurate relative to the largest bin of its frame, not bin by bin
+        assert np.all(err <= 1e-4 * want + 2e-6 * want.max(axis=0, keepdims=True)), float((err / (want + 1e-9)).max())
+    one = ad.spectrogram(xn[0], normalize=False)
+    assert one.shape == (2049, 513)
+    assert np.allclose(one, got[0], rtol=1e-4, atol=2e-6 * got[0].max())
+    mel = td.mel_from_spectrogram(one.reshape(-1))
+    check(oracle, mel[..., 0], oracle.get_spect(xn[0], power=1)[..., 0], what="stored spectrogram -> mel vs path B, power 1")
+    sq = ad.spectrogram(xn[:1], normalize=False, power=2, pad_mode="reflect")
+    want = np.abs(oracle.stft_librosa(xn[0], pad_mode="reflect")) ** 2
+    assert np.all(np.abs(sq[0] - want) <= 2e-4 * want + 4e-6 * want.max(axis=0, keepdims=True))
+    short = ad.spectrogram(xn[:1], n_fft=1024, hop_length=280, normalize=False)     # rides the 4096-point kernel
+    want = np.abs(oracle.stft_librosa(xn[0], n_fft=1024, hop=280))
+    assert short.shape == (1, 513, 515)
+    assert np.all(np.abs(short[0] - want) <= 1e-4 * want + 2e-6 * want.max(axis=0, keepdims=True))
+
+
 # ------------------------------------------------------------------------------------------------ a15 variants
 def test_multi_resolution_variants(oracle, golden_banks, xn):
     """raw_to_mel_rgb / raw_to_mel_dual (tfdataset.py:1818-2004): 1024- and 2048-point STFTs through the 4096-point kernel
