@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
       // 2 * ((v - min) / range) - 1 as one FMA with 2 / range: one division per thread instead of one per element
       // (the pass is MUFU-bound; the result moves by <= 1 ulp of a value in [-1, 1])
       scale = 2.0f / e.x;
-      if (e.x * scale < 2.0f) scale = __uint_as_float(__float_as_uint(scale) + 1u);  // range * scale >= 2: the maximum
+      if (fmaf(e.x, scale, -2.0f) < 0.0f) scale = __uint_as_float(__float_as_uint(scale) + 1u);  // exact: range * scale >= 2, the maximum
       shift = e.y;                                                                  // reaches 1 and is clamped to it
     }
     float m = x[0];  // initial state = inputs[:, 0, :]  (tfpcen.py:92)

@@ -367,6 +367,38 @@ def test_compress(oracle, golden):
 
 
 # ------------------------------------------------------------------------------------------------ errors
+def test_full_size_properties(oracle, bank):
+    """BASELINE.json configs[1] size (4096 clips per launch): properties that need no oracle run at that size.
+    (1) sharding invariance: a clip's features do not depend on its batch (bit-exact against small launches, which the other
+    tests pin to the oracle); (2) homogeneity: without normalisation mel(2x) = 4 mel(x) exactly (powers of two are exact
+    in every stage); (3) the min-max normalisation makes the features invariant to gain and offset; (4) the reference's
+    own run-time invariant on what reaches the model: finite and inside [-1, 1] (tfdataset.py:1442-1472)."""
+    B = 4096
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand((B, 144000), generator=g, device="cuda") - 0.5
+    t = torch.arange(144000, device="cuda", dtype=torch.float32) / 48000.0
+    x += 0.4 * torch.sin(2 * np.pi * (500.0 + 40.0 * torch.arange(B, device="cuda")[:, None] % 9000) * t[None])
+    cfg = rt.FrontendConfig(normalize=True, channels=1, out_layout="btm")
+    plan = rt.get_plan(cfg, 0, bank)
+    full = plan.frontend(x)
+    assert full.shape == (B, 513, 160) and torch.isfinite(full).all()
+    idx = [0, 1, 147, 148, 2047, 4094, 4095]
+    part = plan.frontend(x[idx].contiguous())
+    assert torch.equal(full[idx], part)                                                 # (1)
+    check(oracle, part[:2], np.swapaxes(oracle.raw_to_mel(oracle.normalize(x[:2].cpu().numpy(), np.float32), bank,
+                                                          channels=0), 1, 2), what="full-size launch, clips 0-1")
+    raw_plan = rt.get_plan(cfg.with_(normalize=False), 0, bank)
+    sub = x[:512].contiguous()
+    assert torch.equal(raw_plan.frontend(sub * 2.0), raw_plan.frontend(sub) * 4.0)      # (2)
+    shifted = plan.frontend((sub * 3.0 + 0.25).contiguous())
+    ok, worst = oracle.within_tolerance(shifted.cpu().numpy(), full[:512].cpu().numpy(), 4e-4, 4e-5)
+    assert ok, worst                                                                    # (3): f32 rounding of 3x + 0.25 only
+    out = plan.frontend_pcen(x)
+    assert torch.isfinite(out).all() and out.min().item() == -1.0 and out.max().item() == 1.0   # (4)
+    del x, full, out
+    torch.cuda.empty_cache()
+
+
 def test_errors():
     plan = rt.get_plan(rt.FrontendConfig(), 0)
     with pytest.raises(ValueError):
