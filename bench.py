@@ -42,6 +42,8 @@ BYTES_PER_CLIP = CLIP * 4 + T_FRAMES * N_MELS * 4          # 904 320 B  (SURVEY 
 FLOPS_PER_CLIP = 68e6                                       # FFT 63.0 M + window/power 5.25 M + banded mel
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12           # 74.4
 METRIC = "clips/sec (3 s @48 kHz -> mel+PCEN)"
+WORKLOAD = ("fused normalize -> STFT 4096/281 pad_end -> |z|^2 -> mel 160 -> PCEN (tensor-global min-max), "
+            "batch {B} clips x 3 s @ 48 kHz per GPU")
 
 
 def measured_peaks():
@@ -171,7 +173,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "normalize -> STFT 4096/281 pad_end -> |z|^2 -> mel 160 -> PCEN, 32 clips x 3 s @ 48 kHz per step (CPU)"},
+            "config": {"workload": WORKLOAD.format(B=4096),
+                       "sample": "each step is one batch of 32 clips of that workload on the host cores (BASELINE.json configs[0])"},
             "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -296,7 +299,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"fused normalize -> STFT 4096/281 pad_end -> |z|^2 -> mel 160 -> PCEN (tensor-global min-max), batch {B} clips x 3 s @ 48 kHz per GPU",
+                "config": {"workload": WORKLOAD.format(B=B),
                            "batch_per_gpu": B, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (B * CLIP * 4 / 1e9),
                            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
