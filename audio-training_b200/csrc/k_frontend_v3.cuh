@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   extern __shared__ __align__(128) unsigned char smem[];
   const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
   float4* s_tw4 = reinterpret_cast<float4*>(smem);   // [32 output pairs][64 n2]
-  float* s_win = reinterpret_cast<float*>(smem + L.off_win);
+  float2* s_win2 = reinterpret_cast<float2*>(smem + L.off_win);
   float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
   float* s_exch = reinterpret_cast<float*>(smem + L.off_exch);
   float4* s_melw = reinterpret_cast<float4*>(smem + L.off_melw);
@@ -195,7 +195,11 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   // ---- tables, once per CTA (L2 resident) ------------------------------------------------------------------
   {
     for (int i = tid; i < 2048; i += kVThreads) s_tw4[i] = mj.tw4[i];
-    for (int i = tid; i < kFft; i += kVThreads) s_win[i] = mj.win[i];
+    // window pre-paired for the packed multiply: s_win2[(q / 2) * 64 + t] = (w[64 q + t], w[64 (q + 1) + t]), q even
+    for (int i = tid; i < kFft / 2; i += kVThreads) {
+      const int qh = i >> 6, t = i & 63;
+      s_win2[i] = make_float2(mj.win[128 * qh + t], mj.win[128 * qh + 64 + t]);
+    }
     for (int i = tid; i < 64 * mj.total_quads; i += kVThreads) s_melw[i] = mj.w[i];
     for (int i = tid; i < 64 * kMelMaxSeg; i += kVThreads) s_desc[i] = mj.desc[i];
   }
@@ -249,7 +253,8 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
 #pragma unroll
         for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
           const int n = 64 * q + t64;
-          const cacfe_f2 wv = cacfe_pk(s_win[n], s_win[n + 64]);
+          const float2 w2 = s_win2[(q >> 1) * 64 + t64];
+          const cacfe_f2 wv = cacfe_pk(w2.x, w2.y);
           const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv);
           const cacfe_f2 xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
           re[q] = cacfe_lo(xa);

