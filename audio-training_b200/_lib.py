@@ -66,6 +66,7 @@ PROTOTYPES = {
     "cacfe_plan_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "cacfe_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]),
     "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cacfe_stft_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "cacfe_stft": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "cacfe_mel_from_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cacfe_ema": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),

@@ -192,7 +192,7 @@ class Plan:
             raise ValueError(f"stft: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
         B = raw.shape[0]
         out = torch.empty((B, self.n_bins, self.n_frames), dtype=torch.float32, device=raw.device)
-        ws = self.workspace_for(B)
+        ws = self.workspace(self._lib.cacfe_stft_workspace_bytes(self._handle, B))
         _lib.check(self._lib.cacfe_stft(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
         return out
 

@@ -627,12 +627,30 @@ int cacfe_frontend(cacfe_plan* p, const float* raw, float* feat, int B, void* ws
   return launch_frontend(p, raw, feat, B, p->cfg.out_layout, p->cfg.channels, ws, (cudaStream_t)stream);
 }
 
+constexpr int kStftChunk = 64;  // clips per staging buffer of cacfe_stft
+
+size_t cacfe_stft_workspace_bytes(const cacfe_plan* p, int B) {
+  if (!p || B < 1) return 0;
+  const int nb = B < kStftChunk ? B : kStftChunk;
+  return frontend_ws_bytes(B) + align256((size_t)nb * p->n_bins * p->n_frames * sizeof(float));
+}
+
 int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, void* stream) {
-  if (!p || !raw || !spec) return fail(CACFE_EINVAL, "stft: null argument");
+  if (!p || !raw || !spec || !ws) return fail(CACFE_EINVAL, "stft: null argument");
   if (B < 1) return fail(CACFE_ESHAPE, "stft: B=%d", B);
-  if (p->cfg.normalize && !ws) return fail(CACFE_EINVAL, "stft: workspace required when normalize is set");
   CUDA_TRY(cudaSetDevice(p->device));
-  return launch_frontend(p, raw, spec, B, cacfe::LAYOUT_SPEC, 1, ws, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* staging = (float*)((char*)ws + frontend_ws_bytes(B));
+  const size_t per_clip = (size_t)p->n_bins * p->n_frames;
+  for (int b0 = 0; b0 < B; b0 += kStftChunk) {  // [b][t][k] staging (coalesced from the FFT kernel), then the transpose
+    const int nb = B - b0 < kStftChunk ? B - b0 : kStftChunk;
+    int rc = launch_frontend(p, raw + (size_t)b0 * p->cfg.n_samples, staging, nb, cacfe::LAYOUT_SPEC, 1, ws, st);
+    if (rc != CACFE_OK) return rc;
+    dim3 grid((p->n_bins + 31) / 32, (p->n_frames + 31) / 32, nb);
+    cacfe::spec_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(staging, spec + (size_t)b0 * per_clip, p->n_frames, p->n_bins);
+    if ((rc = check_launch(p, "stft transpose")) != CACFE_OK) return rc;
+  }
+  return CACFE_OK;
 }
 
 int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, int B, int T, void* stream) {

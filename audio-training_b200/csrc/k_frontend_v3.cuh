@@ -316,12 +316,14 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
 
     if (LAYOUT == LAYOUT_SPEC) {
       // ---- spectrogram output (audiodataset.load_data, audiodataset.py:1302-1303): |X| (power 1) or |X|^2 of every bin
-      // of an n_fft-point transform to out[b][k][t]; bins of the 4096-point grid that are not multiples of `ratio`
-      // belong to no bin of the shorter transform.  Rows are 8 bytes per pair here; the six groups of the CTA write the
-      // other 40 bytes of the same 48-byte run within the trip, so the sectors are merged in L2.
+      // of an n_fft-point transform; bins of the 4096-point grid that are not multiples of `ratio` belong to no bin of
+      // the shorter transform.
       const bool row0 = j == 0;
       const int ratio = mj.spec_ratio, n_out = mj.spec_bins;
-      float* obase = a.out + (size_t)b_cur * n_out * a.n_frames + ta;
+      // staged as [b][t][k] (k contiguous: the 64 threads of a group write 256-byte runs); spec_transpose_kernel turns it
+      // into the stored [b][k][t].  A direct [k][t] store writes 8-byte pieces to 2049 different rows per pair (measured:
+      // 11.8 ms instead of 2.6 ms per 1024 clips).
+      float* obase = a.out + ((size_t)b_cur * a.n_frames + ta) * n_out;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const float sr = __shfl_sync(kFullMask, re[63 - (q & 31)], plane);
@@ -341,9 +343,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           }
           const int k = j + 64 * q;
           if (k % ratio == 0) {
-            float* o = obase + (size_t)(k / ratio) * a.n_frames;
+            float* o = obase + k / ratio;
             o[0] = va;
-            if (store_b) o[1] = vb;
+            if (store_b) o[n_out] = vb;
           }
         } else if (row0) {
           // Nyquist bin k = 2048 = row 0, q = 32: Z[2048] pairs with itself
@@ -356,9 +358,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
             va *= 0.25f;
             vb *= 0.25f;
           }
-          float* o = obase + (size_t)(2048 / ratio) * a.n_frames;
+          float* o = obase + 2048 / ratio;
           o[0] = va;
-          if (store_b) o[1] = vb;
+          if (store_b) o[n_out] = vb;
         }
       }
       continue;
@@ -455,6 +457,23 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
     // (the next trip's exchange stores come after release_tile's group barrier: the powers have been consumed by then)
+  }
+}
+
+// [B][T][K] staging -> [B][K][T] (the layout audiowriter stores and tfdataset.read_tfrecord reshapes to, tfdataset.py:1083).
+// 32 x 32 tiles through shared memory, both sides coalesced.  grid = (ceil(K/32), ceil(T/32), B), block = (32, 8).
+__global__ void __launch_bounds__(256) spec_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int K) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * T * K;
+  const int k0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int t = t0 + r, k = k0 + threadIdx.x;
+    tile[r][threadIdx.x] = (t < T && k < K) ? in[base + (size_t)t * K + k] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, t = t0 + threadIdx.x;
+    if (k < K && t < T) out[base + (size_t)k * T + t] = tile[threadIdx.x][r];
   }
 }
 
