@@ -235,12 +235,26 @@ def run_ours(args):
     ms_step = dist_.max_over_ranks(ms_total / args.steps, device)
     value = world * B / (ms_step * 1e-3)
 
+    # ---- DRAM traffic of the dominant kernel: from the committed ncu --set full capture (1024 clips per launch),
+    # scaled to this launch's clip count; None when the summary is not there
+    traffic = None
+    try:
+        import re
+        txt = open(os.path.join(REPO, "profiles", "r01_k1_v3_ncu_summary.txt")).read()
+        rd = float(re.search(r"dram__bytes_read\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
+        wr = float(re.search(r"dram__bytes_write\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
+        traffic = (rd + wr) * 1e6 / 1024.0 * B
+    except Exception:
+        traffic = None
+
     # ---- roofline of the dominant kernel, from the in-region CUDA events --------------------------------------
     k1_avg_ms = k1_ms / max(k1_n, 1)
     achieved = BYTES_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e9
     fp32_achieved = FLOPS_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e12
     roofline = {"kernel": "stft_mel_v3_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
+                                "in profiles/ (1024 clips per launch) scaled to this batch", "peak_kind": peak_kind,
                 "ms_per_launch": k1_avg_ms, "share_of_step": k1_avg_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B,
                 "fp32": {"achieved": fp32_achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
