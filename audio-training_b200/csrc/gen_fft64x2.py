@@ -129,8 +129,8 @@ def main():
     out.append("#ifdef __CUDA_ARCH__")
     out.append("typedef unsigned long long cacfe_f2;")
     out.append('__device__ __forceinline__ cacfe_f2 cacfe_pk(float lo, float hi) { cacfe_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }')
-    out.append('__device__ __forceinline__ float cacfe_lo(cacfe_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }')
-    out.append('__device__ __forceinline__ float cacfe_hi(cacfe_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }')
+    out.append('__device__ __forceinline__ float cacfe_lo(cacfe_f2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }')
+    out.append('__device__ __forceinline__ float cacfe_hi(cacfe_f2 v) { return __uint_as_float((unsigned)(v >> 32)); }')
     out.append('__device__ __forceinline__ cacfe_f2 cacfe_add2(cacfe_f2 a, cacfe_f2 b) { cacfe_f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }')
     out.append('__device__ __forceinline__ cacfe_f2 cacfe_sub2(cacfe_f2 a, cacfe_f2 b) { cacfe_f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }')
     out.append('__device__ __forceinline__ cacfe_f2 cacfe_mul2(cacfe_f2 a, cacfe_f2 b) { cacfe_f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }')
