@@ -328,6 +328,14 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
   if (e == cudaSuccess && p->frontend_ok)
     e = cudaFuncSetAttribute(cacfe::stft_mel_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+  if (e == cudaSuccess) {
+    const int scan_smem = cacfe::kScanWarps * cacfe::kScanMaxRow * (int)sizeof(float);
+    e = cudaFuncSetAttribute(cacfe::pcen_scan_kernel<cacfe::PCEN_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(cacfe::pcen_scan_kernel<cacfe::PCEN_REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(cacfe::pcen_scan_kernel<cacfe::PCEN_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem);
+  }
   if (e == cudaSuccess && p->tc_ok) e = upload((void**)&p->d_tc_w, tc_w.data(), tc_w.size() * sizeof(float));
   if (e == cudaSuccess && p->tc_ok)
     e = upload((void**)&p->d_tc_chunks, p->tc_chunks.data(), p->tc_chunks.size() * sizeof(cacfe::MelTcChunk));
@@ -443,7 +451,10 @@ PcenGrid pcen_grid(long long rows_per_clip) {
 
 size_t pcen_ws_bytes(int B, long long rows_per_clip) {
   const PcenGrid g = pcen_grid(rows_per_clip);
-  return align256((size_t)B * g.gx * sizeof(float2)) + align256((size_t)B * sizeof(float2));
+  const size_t lanes = align256((size_t)B * g.gx * sizeof(float2));
+  // the warp-scan kernel writes one partial per 8 rows; rows <= rows_per_clip per clip whatever the inner size is
+  const size_t scan = align256((size_t)B * ((rows_per_clip + cacfe::kScanWarps - 1) / cacfe::kScanWarps) * sizeof(float2));
+  return (lanes > scan ? lanes : scan) + align256((size_t)B * sizeof(float2));
 }
 
 int compress_blocks(long long entries, long long per_entry) {
@@ -741,6 +752,30 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
   a.T = T;
   a.inner = inner;
   a.rows_per_clip = (int)(outer_per_clip * inner);
+  // time-contiguous rows with a small inner size (the image layout): the warp-scan kernel, one warp per row
+  const long long rows = (long long)B * outer_per_clip;
+  const bool scan = inner <= cacfe::kScanMaxC && (long long)T * inner <= cacfe::kScanMaxRow && T >= 32 &&
+                    (q->norm_scope != CACFE_NORM_CLIP || outer_per_clip % cacfe::kScanWarps == 0);
+  if (scan) {
+    const unsigned ctas = (unsigned)((rows + cacfe::kScanWarps - 1) / cacfe::kScanWarps);
+    const size_t smem = (size_t)cacfe::kScanWarps * T * inner * sizeof(float);
+    if (q->norm_scope == CACFE_NORM_NONE) {
+      cacfe::pcen_scan_kernel<cacfe::PCEN_RAW><<<ctas, cacfe::kScanWarps * 32, smem, st>>>(a, rows, outer_per_clip);
+      return check_launch(p, "pcen (scan)");
+    }
+    if (!ws) return fail(CACFE_EINVAL, "pcen: workspace required for the min-max scope");
+    a.partial = (float2*)ws;
+    float2* ext = (float2*)((char*)ws + align256((size_t)ctas * sizeof(float2)));
+    a.extremes = ext;
+    a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
+    cacfe::pcen_scan_kernel<cacfe::PCEN_REDUCE><<<ctas, cacfe::kScanWarps * 32, smem, st>>>(a, rows, outer_per_clip);
+    if (a.per_clip_extremes)
+      cacfe::minmax_finalize_kernel<<<B, 256, 0, st>>>(a.partial, (int)(outer_per_clip / cacfe::kScanWarps), ext);
+    else
+      cacfe::minmax_finalize_kernel<<<1, 256, 0, st>>>(a.partial, (int)ctas, ext);
+    cacfe::pcen_scan_kernel<cacfe::PCEN_APPLY><<<ctas, cacfe::kScanWarps * 32, smem, st>>>(a, rows, outer_per_clip);
+    return check_launch(p, "pcen (scan)", 3);
+  }
   const PcenGrid g = pcen_grid(a.rows_per_clip);
   dim3 grid(g.gx, B);
   if (q->norm_scope == CACFE_NORM_NONE) {

@@ -147,4 +147,98 @@ __global__ void __launch_bounds__(256) ema_kernel(const PcenArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3b: PCEN for time-contiguous data  x[rows][T][C]  with a small inner size C (the image layout [B][M][T][C] that
+// raw_to_mel / get_spect produce and audiomodel.py:793 hands to the layer): the EMA as a warp-level PARALLEL SCAN.
+//
+// One warp per row.  The row (T * C floats, contiguous) is staged in shared memory with coalesced loads; every lane owns
+// a contiguous run of time steps and
+//   1. folds its run into the affine map  M_out = a * M_in + b   (a = (1-w)^n, b = the run's EMA from a zero state),
+//   2. the 32 maps are combined with a shuffle scan  (a1, b1) o (a2, b2) = (a1 a2, a2 b1 + b2)  so that every lane
+//      learns the smoother's state at the start of its run (the sequence starts from M = x[0], tfpcen.py:92),
+//   3. walks its run again from that state with the reference's own update  w x + (1-w) M  and applies the gain /
+//      bias / root compression, in place in shared memory; the row goes back to HBM with coalesced stores.
+// The smoother's rounding order differs from the sequential tf.scan (survey probe: <= 0.05 of the tolerance budget).
+// The per-lane kernel above walks these rows one 4-byte load per lane and sector (measured 0.7-1.7 TB/s); this one moves
+// whole rows.  Same REDUCE / APPLY / RAW protocol for the min-max scopes.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kScanWarps = 8;
+constexpr int kScanMaxRow = 2048;   // floats per row (T * C) the staging holds
+constexpr int kScanMaxC = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanWarps * 32) pcen_scan_kernel(const PcenArgs a, const long long rows,
+                                                                     const long long rows_per_clip_) {
+  extern __shared__ __align__(16) float s_rows[];   // [kScanWarps][T * C]
+  __shared__ float scratch[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.inner, T = a.T, n = T * C;
+  const long long row = (long long)blockIdx.x * kScanWarps + warp;
+  float mn = INFINITY, mx = -INFINITY;
+  if (row < rows) {
+    float* s = s_rows + (size_t)warp * n;
+    const float* x = a.in + (size_t)row * n;
+    for (int i = lane; i < n; i += 32) s[i] = ld_stream(x + i);
+    __syncwarp();
+    float scale = 1.0f, shift = 0.0f;
+    if (MODE == PCEN_APPLY) {
+      const float2 e = a.extremes[a.per_clip_extremes ? (int)(row / rows_per_clip_) : 0];
+      scale = 2.0f / e.x;
+      if (fmaf(e.x, scale, -2.0f) < 0.0f) scale = __uint_as_float(__float_as_uint(scale) + 1u);
+      shift = e.y;
+    }
+    const int per = (T + 31) / 32;                      // time steps per lane
+    const int t_lo = min(lane * per, T), t_hi = min(t_lo + per, T);
+    for (int c = 0; c < C; ++c) {
+      // 1. this lane's run as an affine map of the incoming state
+      float fa = 1.0f, fb = 0.0f;
+      for (int t = t_lo; t < t_hi; ++t) {
+        fb = __fadd_rn(__fmul_rn(a.w, s[t * C + c]), __fmul_rn(a.one_minus_w, fb));
+        fa *= a.one_minus_w;
+      }
+      // 2. inclusive scan of the maps over the lanes (earlier map applied first)
+      float ia = fa, ib = fb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float pa = __shfl_up_sync(kFullMask, ia, o), pb = __shfl_up_sync(kFullMask, ib, o);
+        if (lane >= o) {
+          ib = fmaf(ia, pb, ib);
+          ia *= pa;
+        }
+      }
+      // exclusive: the composition of all earlier lanes, applied to the initial state x[0]
+      float ea = __shfl_up_sync(kFullMask, ia, 1), eb = __shfl_up_sync(kFullMask, ib, 1);
+      if (lane == 0) {
+        ea = 1.0f;
+        eb = 0.0f;
+      }
+      float m = fmaf(ea, s[c], eb);
+      // 3. the run again, from the right state, with the compression
+      for (int t = t_lo; t < t_hi; ++t) {
+        const float v = s[t * C + c];
+        m = __fadd_rn(__fmul_rn(a.w, v), __fmul_rn(a.one_minus_w, m));
+        float p = pcen_point(v, m, a);
+        if (MODE == PCEN_REDUCE) {
+          mn = fminf(mn, p);
+          mx = fmaxf(mx, p);
+        } else {
+          if (MODE == PCEN_APPLY) p = fminf(fmaf(p - shift, scale, -1.0f), 1.0f);
+          s[t * C + c] = p;
+        }
+      }
+      __syncwarp();   // lane l's first sample of channel c + 1 may be ... (runs are disjoint; kept for the in-place writes)
+    }
+    if (MODE != PCEN_REDUCE) {
+      __syncwarp();
+      float* y = a.out + (size_t)row * n;
+      for (int i = lane; i < n; i += 32) y[i] = s[i];
+    }
+  }
+  if (MODE == PCEN_REDUCE) {
+    block_minmax(mn, mx, scratch);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = make_float2(mn, mx);
+  }
+}
+
 }  // namespace cacfe

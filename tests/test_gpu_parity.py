@@ -328,6 +328,29 @@ def test_pcen_image_extension(oracle, golden):
     check(oracle, got, want, what="rank-4 PCEN")
 
 
+def test_pcen_warp_scan_kernel(oracle, golden):
+    """Time-contiguous layouts [B, M, T, C] (C = 1, 3) and [B, T, 1] go through the warp-level parallel-scan kernel; the
+    lane-per-row kernel ([B, T, F], bit-exact EMA order) is the cross-check."""
+    mel = golden["path_a"]                                               # [2, 160, 513]
+    for C in (1, 3):
+        img = np.repeat(mel[..., None], C, axis=3) * (1.0 + 0.1 * np.arange(C, dtype=np.float32))
+        for scope in ("tensor", "clip", "none"):
+            got = atb.PCEN(norm_scope=scope)(img)
+            if scope == "tensor":
+                want = oracle.pcen(img, axis=2)
+            elif scope == "clip":
+                want = np.stack([oracle.pcen(img[i:i + 1], axis=2)[0] for i in range(2)])
+            else:
+                want = oracle.pcen_raw(img, axis=2)
+            check(oracle, got, want, what=f"scan kernel C={C} scope={scope}")
+    btf = np.swapaxes(mel, 1, 2).copy()                                  # [2, 513, 160]: lane-per-row kernel
+    a = atb.PCEN(norm_scope="none")(btf)
+    b = atb.PCEN(norm_scope="none")(mel[..., None])[..., 0]              # [2, 160, 513, 1]: scan kernel
+    check(oracle, np.swapaxes(b, 1, 2), a, 0.5, what="scan vs sequential EMA order")
+    ema_seq = atb.ExponentialMovingAverage(0.04)(btf, initial_state=btf[:, 0, :])
+    assert np.array_equal(ema_seq, oracle.ema(btf, dtype=np.float32))    # the reference order stays bit-exact
+
+
 def test_frontend_pcen_fused_call(oracle, clips, bank):
     t = torch.from_numpy(clips).cuda()
     plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0, bank)
