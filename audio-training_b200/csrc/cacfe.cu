@@ -18,6 +18,7 @@
 #include "k_frontend.cuh"
 #include "k_frontend_v3.cuh"
 #include "k_melspec.cuh"
+#include "k_melspec_stream.cuh"
 #include "k_melspec_tc.cuh"
 #include "k_pcen.cuh"
 #include "k_sosfilt.cuh"
@@ -73,6 +74,12 @@ struct cacfe_plan {
   float* d_tc_w = nullptr;
   cacfe::MelTcChunk* d_tc_chunks = nullptr;
   int* d_mel_desc = nullptr;
+  // streaming stored-spectrogram path (k_melspec_stream.cuh): per-row records and the 1 / 2 / 4-way band segmentations
+  bool ms_ok = false;
+  int ms_rows = 0;
+  float4* d_ms_rows = nullptr;
+  cacfe::MelStreamSeg ms_segs[3][cacfe::kMsMaxSegs];
+  size_t smem_optin = 0, smem_per_sm = 0;
   bool v3_ok = false;
   bool force_generic = false;  // tests: run the non-streaming kernel on configurations that allow both
   bool frontend_ok = false;
@@ -259,6 +266,76 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
                 "bands per 32-bin chunk", cacfe::kTcMaxN);
   }
 
+  // streaming form of the stored-spectrogram path: every bin feeds at most two adjacent bands (lo, lo + 1), lo never
+  // decreases along k.  Anything else keeps the per-column kernel.
+  std::vector<float4> ms_rows;
+  p->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  p->smem_per_sm = (size_t)prop.sharedMemPerMultiprocessor;
+  p->ms_ok = hi >= lo && p->nnz > 0;
+  {
+    int cur = -1;
+    for (int k = lo; k <= hi && p->ms_ok; ++k) {
+      int m_a = -1, m_b = -1, cnt = 0;
+      for (int m = 0; m < cfg->n_mels; ++m)
+        if (p->bank[(size_t)m * p->n_bins + k] != 0.0f) {
+          if (cnt == 0) m_a = m;
+          m_b = m;
+          ++cnt;
+        }
+      int L;
+      if (cnt == 0) {
+        L = cur < 0 ? 0 : cur;
+      } else if (cnt == 1) {
+        L = std::max(std::max(cur, m_a - 1), 0);
+        if (m_a < L) p->ms_ok = false;
+      } else {
+        L = m_a;
+        if (cnt > 2 || m_b != m_a + 1 || L < cur) p->ms_ok = false;
+      }
+      if (!p->ms_ok) break;
+      cur = L;
+      float4 r;
+      r.x = p->bank[(size_t)L * p->n_bins + k];
+      r.y = L + 1 < cfg->n_mels ? p->bank[(size_t)(L + 1) * p->n_bins + k] : 0.0f;
+      std::memcpy(&r.z, &L, 4);
+      r.w = 0.0f;
+      ms_rows.push_back(r);
+    }
+    p->ms_rows = (int)ms_rows.size();
+  }
+  if (p->ms_ok) {
+    // first / last row of every band (absolute bins); cuts at the band whose first row passes the i-th share of the rows
+    auto first_row = [&](int m) { return bfirst[m] + lo; };
+    auto n_rows_of = [&](int m) { return bofs[m + 1] - bofs[m]; };
+    for (int v = 0; v < 3; ++v) {
+      const int ns = 1 << v;
+      int cut[cacfe::kMsMaxSegs + 1];
+      cut[0] = 0;
+      cut[ns] = cfg->n_mels;
+      for (int i = 1; i < ns; ++i) {
+        const int target = lo + (int)((long long)(hi - lo + 1) * i / ns);
+        int m = cut[i - 1];
+        while (m < cfg->n_mels && (n_rows_of(m) == 0 || first_row(m) < target)) ++m;
+        cut[i] = std::max(m, cut[i - 1]);
+      }
+      for (int i = 0; i < ns; ++i) {
+        cacfe::MelStreamSeg sg;
+        sg.m0 = cut[i];
+        sg.m1 = cut[i + 1];
+        int r0 = p->n_bins, r1 = 0;
+        for (int m = sg.m0; m < sg.m1; ++m)
+          if (n_rows_of(m) > 0) {
+            r0 = std::min(r0, first_row(m));
+            r1 = std::max(r1, first_row(m) + n_rows_of(m));
+          }
+        if (r1 <= r0) r0 = r1 = lo;
+        sg.row0 = r0;
+        sg.row1 = r1;
+        p->ms_segs[v][i] = sg;
+      }
+    }
+  }
+
   // The fused raw->mel kernel exists for n_fft = 4096 (the reference's only shipped configuration); other sizes
   // get a plan for the spectrogram / PCEN / compression entry points and cacfe_frontend refuses them.
   p->k1 = cacfe::k1_smem_layout(cfg->hop, cfg->n_mels, p->nnz, 1);
@@ -341,6 +418,18 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = upload((void**)&p->d_tc_chunks, p->tc_chunks.data(), p->tc_chunks.size() * sizeof(cacfe::MelTcChunk));
   if (e == cudaSuccess && p->tc_ok)
     e = cudaFuncSetAttribute(cacfe::melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kTcSmemBytes);
+  if (e == cudaSuccess && p->ms_ok) e = upload((void**)&p->d_ms_rows, ms_rows.data(), ms_rows.size() * sizeof(float4));
+  if (e == cudaSuccess && p->ms_ok) {
+    const void* kernels[24] = {
+#define CACFE_MS_K(C_) (const void*)cacfe::melspec_stream_kernel<C_, false, 1>, (const void*)cacfe::melspec_stream_kernel<C_, false, 3>, \
+                       (const void*)cacfe::melspec_stream_kernel<C_, false, 0>, (const void*)cacfe::melspec_stream_kernel<C_, true, 1>,  \
+                       (const void*)cacfe::melspec_stream_kernel<C_, true, 3>,  (const void*)cacfe::melspec_stream_kernel<C_, true, 0>
+        CACFE_MS_K(1), CACFE_MS_K(2), CACFE_MS_K(3), CACFE_MS_K(4)
+#undef CACFE_MS_K
+    };
+    for (int q = 0; q < 24 && e == cudaSuccess; ++q)
+      e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+  }
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_w, p->jobs.w.data(), p->jobs.w.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_win_full, win_full.data(), win_full.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
@@ -378,6 +467,7 @@ void cacfe_plan_destroy(cacfe_plan* p) {
   cudaFree(p->d_tw4);
   cudaFree(p->d_win_full);
   cudaFree(p->d_mel_desc);
+  cudaFree(p->d_ms_rows);
   delete p;
 }
 
@@ -701,6 +791,61 @@ int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, in
     const long long grid = (long long)B * t.tiles_per_clip;
     cacfe::melspec_tc_kernel<<<(unsigned)grid, cacfe::kTcThreads, cacfe::kTcSmemBytes, (cudaStream_t)stream>>>(t);
     return check_launch(p, "mel_from_spectrogram (tensor core)");
+  }
+  if (p->ms_ok && !p->force_generic && p->cfg.out_layout == CACFE_LAYOUT_BMTC &&
+      T <= cacfe::kMsConsumers * cacfe::kMsMaxCols) {  // streaming kernel: whole-row TMA chunks
+    // two CTAs per SM (each reserves 1 KB) when that leaves four stages, else one
+    cacfe::MelStreamGeom g = cacfe::melstream_geometry(T, p->ms_rows, std::min(p->smem_optin, p->smem_per_sm / 2 - 1024));
+    int ctas_per_sm = 2;
+    if (g.stages < 4) {
+      g = cacfe::melstream_geometry(T, p->ms_rows, p->smem_optin);
+      ctas_per_sm = 1;
+    }
+    if (g.stages >= 3) {
+      cacfe::MelStreamArgs s{};
+      s.spec = spec;
+      s.out = feat;
+      s.rows = p->d_ms_rows;
+      // enough items for ~6 per CTA, so that the static round-robin ends evenly
+      const long long want = 6LL * ctas_per_sm * p->sm_count;
+      const int v = (long long)B >= want ? 0 : ((long long)B * 2 >= want ? 1 : 2);
+      s.n_segs = 1 << v;
+      for (int i = 0; i < s.n_segs; ++i) s.segs[i] = p->ms_segs[v][i];
+      s.n_items = B * s.n_segs;
+      s.n_rows = p->ms_rows;
+      s.bin_lo = p->bin_lo;
+      s.n_bins = p->n_bins;
+      s.T = T;
+      s.n_mels = p->cfg.n_mels;
+      s.channels = p->cfg.channels;
+      s.stages = g.stages;
+      s.stage_floats = g.stage_floats;
+      s.total_bytes = (size_t)B * p->n_bins * T * sizeof(float);
+      int grid = std::min(s.n_items, ctas_per_sm * p->sm_count);
+      grid -= grid % s.n_segs;   // the kernel's segment rotation needs whole clips per grid stride (n_items is a multiple already)
+      const int cols = (T + cacfe::kMsConsumers - 1) / cacfe::kMsConsumers;
+      const bool p2 = p->cfg.power == 2;
+      cudaStream_t st = (cudaStream_t)stream;
+#define CACFE_MS_LAUNCH2(C_, P_, CH_) cacfe::melspec_stream_kernel<C_, P_, CH_><<<grid, cacfe::kMsThreads, g.smem_bytes, st>>>(s)
+#define CACFE_MS_LAUNCH(C_)                                                                                       \
+  do {                                                                                                            \
+    const int chs = s.channels == 1 ? 1 : (s.channels == 3 ? 3 : 0);                                              \
+    if (p2) {                                                                                                     \
+      if (chs == 1) CACFE_MS_LAUNCH2(C_, true, 1); else if (chs == 3) CACFE_MS_LAUNCH2(C_, true, 3); else CACFE_MS_LAUNCH2(C_, true, 0);     \
+    } else {                                                                                                      \
+      if (chs == 1) CACFE_MS_LAUNCH2(C_, false, 1); else if (chs == 3) CACFE_MS_LAUNCH2(C_, false, 3); else CACFE_MS_LAUNCH2(C_, false, 0);  \
+    }                                                                                                             \
+  } while (0)
+      switch (cols) {
+        case 1: CACFE_MS_LAUNCH(1); break;
+        case 2: CACFE_MS_LAUNCH(2); break;
+        case 3: CACFE_MS_LAUNCH(3); break;
+        default: CACFE_MS_LAUNCH(4); break;
+      }
+#undef CACFE_MS_LAUNCH2
+#undef CACFE_MS_LAUNCH
+      return check_launch(p, "mel_from_spectrogram (stream)");
+    }
   }
   cacfe::MelSpecArgs a;
   a.spec = spec;

@@ -215,6 +215,53 @@ def test_path_c(oracle, golden, xn, bank):
     check(oracle, small, oracle.mel_spec(mag[:1025], 48000, 2048, 278, 96, 100, 11000, 1000, 1), what="mel_spec 2048")
 
 
+def _both_path_c(cfg, bank, spec):
+    plan = rt.Plan(cfg, 0, bank)
+    a = plan.mel_from_spectrogram(spec)
+    plan.force_generic(True)
+    b = plan.mel_from_spectrogram(spec)
+    return a, b
+
+
+@pytest.mark.parametrize("B,T,power,channels", [(5, 513, 1, 1), (3, 513, 2, 3), (1000, 37, 1, 1), (1800, 21, 2, 1), (2, 700, 1, 1)])
+def test_path_c_streaming_kernel(oracle, bank, B, T, power, channels):
+    """melspec_stream_kernel (whole-row TMA chunks, 4 / 2 / 1 band segments per clip by batch size, odd clips start on
+    4-byte boundaries) accumulates along k in the order of the per-column kernel: bit-identical to it, and inside the
+    tolerance of the f64 oracle."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    spec = torch.rand((B, 2049, T), generator=g, device="cuda") * 3.0
+    a, b = _both_path_c(rt.FrontendConfig(power=power, channels=channels), bank, spec)
+    assert a.shape == (B, 160, T, channels)
+    assert torch.equal(a, b)
+    for i in (0, B - 1):
+        want = oracle.mel_from_spectrogram(spec[i].cpu().numpy(), bank, power=power)[..., 0]
+        check(oracle, a[i, ..., channels - 1], want, what="streaming path C vs f64 oracle")
+
+
+def test_path_c_streaming_edges(oracle):
+    """Banks that reach bin 0 and the Nyquist bin on an array that starts and ends off the 16-byte grid: the first and the
+    last chunk cannot be bulk-copied and are loaded by the consumers.  A bank whose bins feed three bands is not of the
+    two-accumulator form: it must take the per-column kernel and still be right."""
+    K, M, T, B = 129, 11, 37, 3
+    k = np.arange(K, dtype=np.float64)[None, :]
+    c = (12.8 * np.arange(M, dtype=np.float64))[:, None]
+    flat = torch.rand(B * K * T + 3, device="cuda")
+    spec = flat[1:1 + B * K * T].view(B, K, T)
+    assert spec.data_ptr() % 16 == 4
+    for width in (12.8, 20.0):
+        fb = np.maximum(0.0, 1.0 - np.abs(k - c) / width).astype(np.float32)
+        assert fb[0, 0] > 0 and fb[-1, -1] > 0
+        cfg = rt.FrontendConfig(n_fft=256, hop=64, n_mels=M, power=2, channels=3)
+        a, b = _both_path_c(cfg, fb, spec)
+        assert torch.equal(a, b)
+        want = np.einsum("mk,bkt->bmt", fb.astype(np.float64), spec.cpu().numpy().astype(np.float64) ** 2)
+        check(oracle, a[..., 1], want, what=f"custom bank, width {width}")
+    gap = np.maximum(0.0, 1.0 - np.abs(k - c) / 12.8).astype(np.float32)
+    gap[[3, 4]] = 0.0                                                    # empty bands (custommel.py:45-52 warns about these)
+    a, b = _both_path_c(rt.FrontendConfig(n_fft=256, hop=64, n_mels=M, power=1, channels=1), gap, spec)
+    assert torch.equal(a, b) and float(a[:, 3:5].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("power,layout,channels", [(1, "bmtc", 1), (2, "bmtc", 3), (1, "btm", 1)])
 def test_path_c_tensor_core(oracle, xn, bank, power, layout, channels):
     """tcgen05 banded 3xTF32 GEMM (k_melspec_tc.cuh) against the f64 oracle and against the banded FP32 kernel."""
