@@ -227,3 +227,56 @@ def test_multi_resolution_variants_match_reference_code(oracle, golden_banks):
     f64 = oracle.raw_to_mel_rgb(x, w4096, wlo, whi)                          # the f64 ground truth sits inside the budget too
     ok, worst = oracle.within_tolerance(g["rgb"], f64)
     assert ok, worst
+
+
+def test_stft_restatements_against_independent_libraries(oracle, clips):
+    """The oracle's restatements of tf.signal.stft / librosa.stft are documentation-derived (TensorFlow and librosa cannot
+    be installed here).  Two independent third-party STFTs that ARE installed follow the same published conventions and
+    pin the framing, the periodic Hann window and the transform: torch.stft (written to match librosa: center,
+    pad_mode, hop, window) and scipy.signal.ShortTimeFFT."""
+    import torch
+    import scipy.signal as ss
+    x = oracle.normalize(clips[:1], np.float32)[0].astype(np.float64)
+    xt = torch.from_numpy(x)
+    win = torch.hann_window(4096, periodic=True, dtype=torch.float64)
+    assert np.allclose(win.numpy(), oracle.hann_periodic(4096), atol=1e-15)
+    assert np.allclose(ss.get_window("hann", 4096, fftbins=True), oracle.hann_periodic(4096), atol=1e-15)
+    scale = np.abs(oracle.stft_librosa(x)).max()
+    for mode in ("constant", "reflect"):                               # librosa >= 0.10 / < 0.10 pad_mode (Appendix B)
+        want = torch.stft(xt, 4096, 281, window=win, center=True, pad_mode=mode, return_complex=True).numpy()
+        got = oracle.stft_librosa(x, pad_mode=mode)
+        assert got.shape == want.shape == (2049, 513)
+        assert np.abs(got - want).max() <= 1e-10 * scale
+    # tf.signal.stft(pad_end=True): T = ceil(N / hop) left-aligned frames, zeros past the end, [T, bins]
+    T = -(-len(x) // 281)
+    padded = torch.cat([xt, torch.zeros(281 * (T - 1) + 4096 - len(x), dtype=torch.float64)])
+    want = torch.stft(padded, 4096, 281, window=win, center=False, return_complex=True).numpy().T
+    got = oracle.stft_tf(x)
+    assert got.shape == want.shape == (513, 2049)
+    assert np.abs(got - want).max() <= 1e-10 * scale
+    # the no-pad variant of raw_to_mel_dual (tfdataset.py:1838-1854): 2048 / 278 -> 511 frames
+    want = torch.stft(xt, 2048, 278, window=torch.hann_window(2048, periodic=True, dtype=torch.float64), center=False,
+                      return_complex=True).numpy().T
+    got = oracle.stft_tf(x, 2048, 278, pad_end=False)
+    assert got.shape == want.shape == (511, 1025) and np.abs(got - want).max() <= 1e-10 * scale
+    # scipy's ShortTimeFFT: frame p is centred on sample p * hop (the librosa convention); compare the interior frames
+    # (phase_shift=None: phase referred to the first sample of the frame, as librosa and TensorFlow do)
+    sft = ss.ShortTimeFFT(ss.get_window("hann", 4096, fftbins=True), hop=281, fs=48000, fft_mode="onesided", phase_shift=None)
+    S = sft.stft(x)                                                    # [bins, p_min..p_max]
+    p0 = -sft.p_min
+    got = oracle.stft_librosa(x)
+    assert np.abs(S[:, p0:p0 + 513] - got).max() <= 1e-10 * scale
+
+
+def test_ema_restatement_against_scipy_lfilter(oracle):
+    """tf.scan with initializer x[0] (tfpcen.py:33-38) is the one-pole IIR y[t] = w x[t] + (1 - w) y[t-1], y[-1] = x[0]:
+    scipy.signal.lfilter with that initial state is an independent statement of it."""
+    import scipy.signal as ss
+    x = np.random.default_rng(5).random((3, 200, 7))
+    w = 0.04
+    want = np.empty_like(x)
+    for b in range(3):
+        for f in range(7):
+            zi = ss.lfiltic([w], [1.0, -(1.0 - w)], y=[x[b, 0, f]])
+            want[b, :, f] = ss.lfilter([w], [1.0, -(1.0 - w)], x[b, :, f], zi=zi)[0]
+    assert np.allclose(oracle.ema(x, w), want, rtol=1e-12, atol=1e-14)
