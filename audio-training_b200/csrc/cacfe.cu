@@ -762,7 +762,7 @@ int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, vo
     const int nb = B - b0 < kStftChunk ? B - b0 : kStftChunk;
     int rc = launch_frontend(p, raw + (size_t)b0 * p->cfg.n_samples, staging, nb, cacfe::LAYOUT_SPEC, 1, ws, st);
     if (rc != CACFE_OK) return rc;
-    dim3 grid((p->n_bins + 31) / 32, (p->n_frames + 31) / 32, nb);
+    dim3 grid((p->n_bins + cacfe::kTrTile - 1) / cacfe::kTrTile, (p->n_frames + cacfe::kTrTile - 1) / cacfe::kTrTile, nb);
     cacfe::spec_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(staging, spec + (size_t)b0 * per_clip, p->n_frames, p->n_bins);
     if ((rc = check_launch(p, "stft transpose")) != CACFE_OK) return rc;
   }
