@@ -235,6 +235,21 @@ class Plan:
                                         _ptr(ws), _stream(self.device)))
         return out
 
+    def pcen_backward(self, x, grad_out, params=None, time_axis=1):
+        """Gradients of `pcen` (tfpcen.py:89-110) -> (dL/dx, dL/d[gain, bias, root, smooth] as a device tensor of 4)."""
+        x = self._check_in(x, "pcen_backward")
+        grad_out = self._check_in(grad_out, "pcen_backward")
+        if grad_out.shape != x.shape:
+            raise ValueError(f"pcen_backward: grad_out {tuple(grad_out.shape)} != x {tuple(x.shape)}")
+        B, opc, T, inner = _split_axes(x, time_axis)
+        dx = torch.empty_like(x)
+        dparams = torch.empty(4, dtype=torch.float32, device=x.device)
+        params = params or pcen_params()
+        ws = self.workspace(self._lib.cacfe_pcen_backward_workspace_bytes(B, opc, inner))
+        _lib.check(self._lib.cacfe_pcen_backward(self._handle, ctypes.byref(params), _ptr(x), _ptr(grad_out), _ptr(dx),
+                                                 _ptr(dparams), B, opc, T, inner, _ptr(ws), _stream(self.device)))
+        return dx, dparams
+
     def compress(self, x, mode, param=0.0, per_clip=False):
         x = self._check_in(x, "compress")
         entries = x.shape[0] if per_clip else 1

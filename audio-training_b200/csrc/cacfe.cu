@@ -21,6 +21,7 @@
 #include "k_melspec_stream.cuh"
 #include "k_melspec_tc.cuh"
 #include "k_pcen.cuh"
+#include "k_pcen_bwd.cuh"
 #include "k_sosfilt.cuh"
 
 namespace {
@@ -951,6 +952,75 @@ int cacfe_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* in, float
   if (q->norm_scope < 0 || q->norm_scope > 2) return fail(CACFE_EINVAL, "pcen: unknown norm_scope");
   CUDA_TRY(cudaSetDevice(p->device));
   return launch_pcen(p, q, in, out, B, outer_per_clip, T, inner, ws, (cudaStream_t)stream);
+}
+
+// ---- PCEN backward -----------------------------------------------------------------------------
+static size_t pcen_bwd_layout(int B, long long rows_per_clip, size_t off[4]) {
+  const PcenGrid g = pcen_grid(rows_per_clip);
+  const int gx2 = (int)((rows_per_clip + cacfe::kBwdThreads - 1) / cacfe::kBwdThreads);
+  const int gmax = g.gx > gx2 ? g.gx : gx2;
+  size_t o = 0;
+  off[0] = o; o += align256((size_t)B * g.gx * sizeof(float2));          // forward block extremes
+  off[1] = o; o += align256((size_t)B * sizeof(float2));                 // (mn, mx) per entry
+  off[2] = o; o += align256((size_t)B * gmax * 4 * sizeof(double));      // block partial sums
+  off[3] = o; o += align256((size_t)B * sizeof(float4));                 // folded min-max terms
+  return o;
+}
+
+size_t cacfe_pcen_backward_workspace_bytes(int B, long long outer_per_clip, int inner) {
+  if (B < 1 || outer_per_clip < 1 || inner < 1) return 0;
+  size_t off[4];
+  return pcen_bwd_layout(B, outer_per_clip * inner, off);
+}
+
+int cacfe_pcen_backward(cacfe_plan* p, const cacfe_pcen_params* q, const float* x, const float* grad_out, float* grad_x,
+                        float* grad_params, int B, long long outer_per_clip, int T, int inner, void* ws, void* stream) {
+  if (!p || !q || !x || !grad_out || !grad_x || !grad_params || !ws) return fail(CACFE_EINVAL, "pcen_backward: null argument");
+  if (B < 1 || B > 65535 || T < 1 || inner < 1 || outer_per_clip < 1 || outer_per_clip * inner > 2147483647LL)
+    return fail(CACFE_ESHAPE, "pcen_backward: bad shape");
+  if (T > cacfe::kBwdSeg * cacfe::kBwdMaxSeg)
+    return fail(CACFE_ESHAPE, "pcen_backward: T=%d exceeds %d time steps", T, cacfe::kBwdSeg * cacfe::kBwdMaxSeg);
+  if (q->norm_scope < 0 || q->norm_scope > 2) return fail(CACFE_EINVAL, "pcen_backward: unknown norm_scope");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  cacfe::PcenBwdArgs a{};
+  int rc = fill_pcen_args(q, a.f);
+  if (rc != CACFE_OK) return rc;
+  a.f.in = x;
+  a.f.T = T;
+  a.f.inner = inner;
+  a.f.rows_per_clip = (int)(outer_per_clip * inner);
+  a.g = grad_out;
+  a.dx = grad_x;
+  a.gain_raw = q->gain;
+  a.root_raw = q->root;
+  a.smooth_raw = q->smooth;
+  a.scope = q->norm_scope;
+  size_t off[4];
+  pcen_bwd_layout(B, a.f.rows_per_clip, off);
+  char* w = (char*)ws;
+  float2* extremes = (float2*)(w + off[1]);
+  double* partial = (double*)(w + off[2]);
+  float4* fold = (float4*)(w + off[3]);
+  a.extremes = extremes;
+  a.partial = partial;
+  a.fold = fold;
+  const PcenGrid g = pcen_grid(a.f.rows_per_clip);
+  int launches = 2;
+  if (q->norm_scope != CACFE_NORM_NONE) {
+    const int entries = q->norm_scope == CACFE_NORM_CLIP ? B : 1;
+    const int per_entry = q->norm_scope == CACFE_NORM_CLIP ? g.gx : B * g.gx;
+    a.f.partial = (float2*)(w + off[0]);
+    cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, B), g.block, 0, st>>>(a.f);
+    cacfe::minmax_fold_raw_kernel<<<entries, 256, 0, st>>>(a.f.partial, per_entry, extremes);
+    cacfe::pcen_bwd_reduce_kernel<<<dim3(g.gx, B), g.block, 0, st>>>(a);
+    cacfe::pcen_bwd_fold_kernel<<<entries, 32, 0, st>>>(partial, per_entry, extremes, fold);
+    launches += 4;
+  }
+  const int gx2 = (int)((a.f.rows_per_clip + cacfe::kBwdThreads - 1) / cacfe::kBwdThreads);
+  cacfe::pcen_bwd_kernel<<<dim3(gx2, B), cacfe::kBwdThreads, 0, st>>>(a);
+  cacfe::pcen_bwd_params_kernel<<<1, 32, 0, st>>>(partial, B * gx2, q->gain, q->root, q->smooth, grad_params);
+  return check_launch(p, "pcen_backward", launches);
 }
 
 int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float* out, long long entries,

@@ -1,7 +1,8 @@
 """Drop-in for the reference's `tfpcen` module (tfpcen.py:8-110): ExponentialMovingAverage, PCEN, normalize_minmax.
 
 The layers keep the reference's constructor arguments, weight names, creation order and initial values so
-checkpoints map one to one; `__call__` runs the CUDA kernels (forward only -- the front-end is used frozen).
+checkpoints map one to one; `__call__` runs the CUDA kernels.  `PCENTrainable` is the same layer as a torch module whose
+backward also runs on our kernels (cacfe_pcen_backward) -- for callers that train the front-end's four scalars.
 """
 from __future__ import annotations
 
@@ -86,6 +87,61 @@ class PCEN:
         return restore(_plan(t.device.index).pcen(t, self.params(), axis))
 
     __call__ = call
+
+
+class _PCENFunction:
+    """torch.autograd.Function built lazily (torch is imported by _runtime already; kept out of module import order)."""
+    _fn = None
+
+    @classmethod
+    def get(cls):
+        if cls._fn is not None:
+            return cls._fn
+        import torch
+
+        class PCENFunction(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, gain, bias, root, smooth, eps, norm_scope, time_axis):
+                plan = _plan(x.device.index)
+                p = rt.pcen_params(float(gain), float(bias), float(root), float(smooth), eps, norm_scope)
+                ctx.save_for_backward(x)
+                ctx.cfg = (p, time_axis, plan)
+                return plan.pcen(x, p, time_axis)
+
+            @staticmethod
+            def backward(ctx, grad_out):
+                (x,) = ctx.saved_tensors
+                p, time_axis, plan = ctx.cfg
+                dx, dp = plan.pcen_backward(x, grad_out.contiguous(), p, time_axis)
+                return dx, dp[0:1], dp[1:2], dp[2:3], dp[3:4], None, None, None
+
+        cls._fn = PCENFunction
+        return PCENFunction
+
+
+def PCENTrainable(norm_scope="tensor"):
+    """tfpcen.PCEN as a torch.nn.Module: parameters gain / bias / root / smooth (+ the unused a_power, Q12) with the
+    reference's initial values; forward and backward both on the CUDA kernels."""
+    import torch
+
+    class _PCENTrainable(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gain = torch.nn.Parameter(torch.full((1,), 0.98))
+            self.bias = torch.nn.Parameter(torch.full((1,), 2.0))
+            self.root = torch.nn.Parameter(torch.full((1,), 2.0))
+            self.smooth = torch.nn.Parameter(torch.full((1,), 0.04))
+            self.a_power = torch.nn.Parameter(torch.full((1,), -1.0))
+            self.eps = 1e-6
+            self.norm_scope = norm_scope
+
+        def forward(self, x):
+            if x.dim() not in (3, 4):
+                raise ValueError("PCEN: expected [batch, time, filters] (or the rank-4 image extension)")
+            return _PCENFunction.get().apply(x.contiguous(), self.gain, self.bias, self.root, self.smooth, self.eps,
+                                             self.norm_scope, 1 if x.dim() == 3 else 2)
+
+    return _PCENTrainable()
 
 
 def normalize_minmax(data):

@@ -162,6 +162,14 @@ int cacfe_ema(cacfe_plan* plan, float smooth, const float* in_dev, float* out_de
 int cacfe_pcen(cacfe_plan* plan, const cacfe_pcen_params* params, const float* in_dev, float* out_dev, int B,
                long long outer_per_clip, int T, int inner, void* workspace_dev, void* stream);
 
+/* ---- backward of PCEN.call (tfpcen.py:89-99 incl. normalize_minmax :105-110), what TensorFlow's autodiff
+ * computes for that graph.  x_dev, grad_out_dev, grad_x_dev: [B * outer_per_clip][T][inner]; grad_params_dev: device float[4] =
+ * dL/d(gain, bias, root, smooth) (0 for a parameter that sits outside its clip range).  T <= 2048. */
+size_t cacfe_pcen_backward_workspace_bytes(int B, long long outer_per_clip, int inner);
+int cacfe_pcen_backward(cacfe_plan* plan, const cacfe_pcen_params* params, const float* x_dev, const float* grad_out_dev,
+                        float* grad_x_dev, float* grad_params_dev, int B, long long outer_per_clip, int T, int inner,
+                        void* workspace_dev, void* stream);
+
 /* ---- a12-a14: point-wise compression with a tensor- (entries = 1) or clip-wide (entries = B) statistic. */
 int cacfe_compress(cacfe_plan* plan, int mode, float param, const float* in_dev, float* out_dev, long long entries,
                    long long per_entry, void* workspace_dev, void* stream);

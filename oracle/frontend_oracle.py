@@ -346,6 +346,38 @@ def pcen(x, gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, dtype=np.float
 # --------------------------------------------------------------------------------------
 # a13 / a14 and friends
 # --------------------------------------------------------------------------------------
+def pcen_backward(x, grad_out, gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, scope="tensor", axis=1):
+    """Gradients of PCEN.call (tfpcen.py:89-99 with normalize_minmax :105-110) by reverse-mode autodiff of the very graph
+    the reference builds -- tf.minimum / tf.maximum / clip_by_value on the scalars, the scan as a sequential loop with
+    initial state inputs[:, 0], reduce_min / reduce_max in the min-max -- evaluated in float64 with torch.autograd (TensorFlow
+    cannot be imported here; the two autodiffs implement the same calculus, ties in min / max share the gradient equally in
+    both).  -> (dL/dx, [dL/dgain, dL/dbias, dL/droot, dL/dsmooth]).  scope: "tensor" (the reference), "clip", "none"."""
+    import torch
+    xt = torch.tensor(np.asarray(x, dtype=np.float64), requires_grad=True)
+    par = [torch.tensor([float(v)], dtype=torch.float64, requires_grad=True) for v in (gain, bias, root, smooth)]
+    g_, b_, r_, s_ = par
+    gg = torch.minimum(g_, torch.ones(1, dtype=torch.float64))
+    rr = torch.maximum(r_, torch.ones(1, dtype=torch.float64))
+    w = torch.clamp(s_, 0.0, 1.0)
+    xm = torch.movedim(xt, axis, 0)
+    state = xm[0]
+    ms = []
+    for t in range(xm.shape[0]):
+        state = w * xm[t] + (1.0 - w) * state
+        ms.append(state)
+    m = torch.movedim(torch.stack(ms, 0), 0, axis)
+    out = (xt / (eps + m) ** gg + b_) ** (1.0 / rr) - b_ ** (1.0 / rr)
+    if scope == "tensor":
+        out = 2 * ((out - out.min()) / (out.max() - out.min())) - 1
+    elif scope == "clip":
+        dims = tuple(range(1, out.dim()))
+        mn, mx = out.amin(dims, keepdim=True), out.amax(dims, keepdim=True)
+        out = 2 * ((out - mn) / (mx - mn)) - 1
+    out.backward(torch.tensor(np.asarray(grad_out, dtype=np.float64)))
+    zero = torch.zeros(1, dtype=torch.float64)
+    return xt.grad.numpy(), np.array([float((q.grad if q.grad is not None else zero)[0]) for q in par])
+
+
 def power_to_db(mel, dtype=np.float64):
     """tfdataset.py:1906-1913: 10log10(max(1e-10,x)) - 10log10(max(1e-10,max x)), floored at
     (max of the result) - 80, tensor-global."""

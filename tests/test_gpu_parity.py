@@ -483,3 +483,50 @@ def test_errors():
         td.raw_to_mel_dual(torch.zeros(1, 144000, device="cuda"), None)
     assert plan.bin_range() == (9, 938)
     assert plan.launch_count() >= 0
+
+
+# ------------------------------------------------------------------------------------------------ PCEN backward (8f rank 4)
+@pytest.mark.parametrize("shape,axis,scope,kw", [
+    ((3, 70, 40), 1, "tensor", {}),
+    ((3, 70, 40), 1, "clip", {}),
+    ((3, 70, 40), 1, "none", {}),
+    ((2, 513, 160), 1, "tensor", {}),
+    ((2, 6, 45, 3), 2, "tensor", {}),                                  # the rank-4 image extension
+    ((2, 33, 17), 1, "tensor", dict(gain=0.7, bias=1.5, root=3.0, smooth=0.3)),
+    ((2, 33, 17), 1, "none", dict(gain=1.3, root=0.5, smooth=1.5)),      # all three outside their clip range: zero gradient
+])
+def test_pcen_backward(oracle, shape, axis, scope, kw):
+    """cacfe_pcen_backward against float64 reverse-mode autodiff of the reference's graph (oracle.pcen_backward)."""
+    rng = np.random.default_rng(abs(hash((shape, scope))) % 2**31)
+    x = (rng.random(shape) ** 3 * 5.0 + 1e-3).astype(np.float32)         # mel-like: positive, heavy-tailed
+    g = rng.standard_normal(shape).astype(np.float32)
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    p = rt.pcen_params(norm_scope=scope, **kw)
+    dx, dp = plan.pcen_backward(torch.from_numpy(x).cuda(), torch.from_numpy(g).cuda(), p, axis)
+    want_dx, want_dp = oracle.pcen_backward(x, g, scope=scope, axis=axis, **kw)
+    dx, dp = dx.cpu().numpy(), dp.cpu().numpy()
+    scale = np.abs(want_dx).max()
+    err = np.abs(dx - want_dx)
+    assert np.all(err <= 2e-4 * np.abs(want_dx) + 2e-5 * scale), float((err / (np.abs(want_dx) + 1e-1 * scale)).max())
+    for name, a, b in zip(("gain", "bias", "root", "smooth"), dp, want_dp):
+        # floor: FP32 rounding of every element's contribution (a clipped root makes the bias terms cancel to rounding only)
+        assert abs(a - b) <= 5e-4 * abs(b) + 1e-4 * np.abs(want_dp).max() + 2e-7 * np.abs(g).sum(), (name, a, b)
+    if kw.get("gain", 0) > 1:
+        assert dp[0] == 0 and dp[2] == 0 and dp[3] == 0
+
+
+def test_pcen_trainable_module(oracle):
+    """tfpcen.PCENTrainable: torch autograd through our forward and backward kernels."""
+    from audio_training_b200 import tfpcen
+    layer = tfpcen.PCENTrainable().cuda()
+    assert [n for n, _ in layer.named_parameters()] == ["gain", "bias", "root", "smooth", "a_power"]
+    x = (torch.rand(2, 60, 24, device="cuda") * 4 + 0.01).requires_grad_(True)
+    y = layer(x)
+    assert np.allclose(y.detach().cpu().numpy(), oracle.pcen(x.detach().cpu().numpy()), rtol=1e-4, atol=1e-5)
+    wgt = torch.linspace(-1, 1, y.numel(), device="cuda").view_as(y)
+    (y * wgt).sum().backward()
+    want_dx, want_dp = oracle.pcen_backward(x.detach().cpu().numpy(), wgt.cpu().numpy())
+    assert np.allclose(x.grad.cpu().numpy(), want_dx, rtol=2e-4, atol=2e-5 * np.abs(want_dx).max())
+    got = [float(layer.gain.grad), float(layer.bias.grad), float(layer.root.grad), float(layer.smooth.grad)]
+    assert np.allclose(got, want_dp, rtol=5e-4, atol=1e-4 * np.abs(want_dp).max())
+    assert layer.a_power.grad is None                                    # declared, never used (Q12)

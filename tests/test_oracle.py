@@ -280,3 +280,22 @@ def test_ema_restatement_against_scipy_lfilter(oracle):
             zi = ss.lfiltic([w], [1.0, -(1.0 - w)], y=[x[b, 0, f]])
             want[b, :, f] = ss.lfilter([w], [1.0, -(1.0 - w)], x[b, :, f], zi=zi)[0]
     assert np.allclose(oracle.ema(x, w), want, rtol=1e-12, atol=1e-14)
+
+
+def test_pcen_backward_oracle_against_finite_differences(oracle):
+    """oracle.pcen_backward (float64 autodiff of the reference's graph) against central differences of oracle.pcen."""
+    x = np.random.default_rng(0).random((2, 20, 5)) + 0.01
+    g = np.random.default_rng(1).standard_normal((2, 20, 5))
+    dx, dp = oracle.pcen_backward(x, g)
+    f = lambda xx=x, **kw: float((oracle.pcen(xx, **kw) * g).sum())
+    h = 1e-6
+    fd = [(f(gain=0.98 + h) - f(gain=0.98 - h)) / (2 * h), (f(bias=2 + h) - f(bias=2 - h)) / (2 * h),
+          (f(root=2 + h) - f(root=2 - h)) / (2 * h), (f(smooth=0.04 + h) - f(smooth=0.04 - h)) / (2 * h)]
+    assert np.allclose(dp, fd, rtol=1e-5, atol=1e-7)
+    for idx in [(0, 0, 0), (1, 7, 3), (0, 19, 4)]:
+        xp, xm = x.copy(), x.copy()
+        xp[idx] += h
+        xm[idx] -= h
+        assert abs((f(xp) - f(xm)) / (2 * h) - dx[idx]) <= 1e-5 * max(1.0, abs(dx[idx]))
+    _, clipped = oracle.pcen_backward(x, g, gain=1.2, root=0.8, smooth=1.5, scope="none")
+    assert clipped[0] == 0 and clipped[2] == 0 and clipped[3] == 0       # (and root clipped to 1 removes the bias term too)
