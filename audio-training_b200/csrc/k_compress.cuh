@@ -28,12 +28,27 @@ __global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ in
   float mn = INFINITY, mx = -INFINITY;
   double s = 0.0, ss = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_entry; i += stride) {
-    const float v = ld_stream(x + i);
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto take = [&](float v) {
     mn = fminf(mn, v);
     mx = fmaxf(mx, v);
     s += (double)v;
     ss += (double)v * (double)v;
+  };
+  if ((per_entry & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {  // 16-byte loads, four in flight per thread
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = per_entry >> 2;
+#pragma unroll 4
+    for (long long i = first; i < n4; i += stride) {
+      const float4 v = ld_stream4(x4 + i);
+      take(v.x);
+      take(v.y);
+      take(v.z);
+      take(v.w);
+    }
+  } else {
+#pragma unroll 4
+    for (long long i = first; i < per_entry; i += stride) take(ld_stream(x + i));
   }
   block_minmax(mn, mx, scratch);
   s = warp_sum(s);
@@ -107,19 +122,25 @@ __global__ void __launch_bounds__(256) compress_kernel(const float* __restrict__
     c1 = (float)sqrt(var) + 1e-7f;  // keras.backend.epsilon()
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_entry; i += stride) {
-    const float v = ld_stream(x + i);
-    float r;
-    if (MODE == COMPRESS_MAG_POW) {
-      r = exp2f(param * log2f(v));  // v ** param for v >= 0 (0 -> 0, like tf.pow)
-    } else if (MODE == COMPRESS_POWER_TO_DB) {
-      r = fmaxf(10.0f * log10f(fmaxf(1e-10f, v)) - c0, -80.0f);
-    } else if (MODE == COMPRESS_MINMAX) {
-      r = 2.0f * ((v - c0) / c1) - 1.0f;
-    } else {
-      r = (v - c0) / c1;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto point = [&](float v) -> float {
+    if (MODE == COMPRESS_MAG_POW) return exp2f(param * log2f(v));  // v ** param for v >= 0 (0 -> 0, like tf.pow)
+    if (MODE == COMPRESS_POWER_TO_DB) return fmaxf(10.0f * log10f(fmaxf(1e-10f, v)) - c0, -80.0f);
+    if (MODE == COMPRESS_MINMAX) return 2.0f * ((v - c0) / c1) - 1.0f;
+    return (v - c0) / c1;
+  };
+  if ((per_entry & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    const long long n4 = per_entry >> 2;
+#pragma unroll 4
+    for (long long i = first; i < n4; i += stride) {
+      const float4 v = ld_stream4(x4 + i);
+      y4[i] = make_float4(point(v.x), point(v.y), point(v.z), point(v.w));
     }
-    y[i] = r;
+  } else {
+#pragma unroll 4
+    for (long long i = first; i < per_entry; i += stride) y[i] = point(ld_stream(x + i));
   }
 }
 
