@@ -250,6 +250,35 @@ class Plan:
                                                  _ptr(dparams), B, opc, T, inner, _ptr(ws), _stream(self.device)))
         return dx, dparams
 
+    def signal_components(self, spec, open_size=4, dilate=(6, 42), erode=(3, 3), max_components=8192, debug=False):
+        """identifytracks.signal_noise's array part (identifytracks.py:79-106) on a magnitude spectrogram [K, T]:
+        -> stats [n, 5] int32 rows (x, y, w, h, area) in OpenCV's label order (background row omitted), and with
+        debug=True also the final mask, the thresholded mask and the two median vectors (device tensors)."""
+        spec = self._check_in(spec, "signal_components")
+        if spec.dim() != 2:
+            raise ValueError(f"signal_components: expected [bins, frames], got {tuple(spec.shape)}")
+        K, T = spec.shape
+        dev = spec.device
+        comps = torch.empty((max_components, 6), dtype=torch.int32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        mask = torch.empty((K, T), dtype=torch.uint8, device=dev) if debug else None
+        raw = torch.empty((K, T), dtype=torch.uint8, device=dev) if debug else None
+        rm = torch.empty(K, dtype=torch.float32, device=dev) if debug else None
+        cm = torch.empty(T, dtype=torch.float32, device=dev) if debug else None
+        ws = self.workspace(self._lib.cacfe_signal_workspace_bytes(K, T))
+        _lib.check(self._lib.cacfe_signal_components(self._handle, _ptr(spec), K, T, int(open_size), int(dilate[0]), int(dilate[1]),
+                                                     int(erode[0]), int(erode[1]), _ptr(mask), _ptr(raw), _ptr(rm), _ptr(cm),
+                                                     _ptr(comps), max_components, _ptr(count), _ptr(ws), _stream(self.device)))
+        n = int(count.item())
+        if n > max_components:
+            raise RuntimeError(f"signal_components: {n} components exceed max_components={max_components}")
+        c = comps[:n].cpu().numpy()
+        c = c[np.argsort(c[:, 5], kind="stable")]
+        stats = np.stack([c[:, 0], c[:, 1], c[:, 2] - c[:, 0] + 1, c[:, 3] - c[:, 1] + 1, c[:, 4]], axis=1).astype(np.int32)
+        if debug:
+            return stats, {"mask": mask, "raw_mask": raw, "row_medians": rm, "column_medians": cm}
+        return stats
+
     def compress(self, x, mode, param=0.0, per_clip=False):
         x = self._check_in(x, "compress")
         entries = x.shape[0] if per_clip else 1

@@ -23,6 +23,7 @@
 #include "k_pcen.cuh"
 #include "k_pcen_bwd.cuh"
 #include "k_sosfilt.cuh"
+#include "k_signal.cuh"
 
 namespace {
 
@@ -1021,6 +1022,99 @@ int cacfe_pcen_backward(cacfe_plan* p, const cacfe_pcen_params* q, const float* 
   cacfe::pcen_bwd_kernel<<<dim3(gx2, B), cacfe::kBwdThreads, 0, st>>>(a);
   cacfe::pcen_bwd_params_kernel<<<1, 32, 0, st>>>(partial, B * gx2, q->gain, q->root, q->smooth, grad_params);
   return check_launch(p, "pcen_backward", launches);
+}
+
+// ---- identifytracks.signal_noise, spectrogram -> connected components ---------------------------
+static size_t signal_layout(int K, int T, size_t off[9]) {
+  const size_t n = (size_t)K * T;
+  size_t o = 0;
+  off[0] = o; o += align256(1024 * sizeof(cacfe::Stats));   // block partials of the global maximum
+  off[1] = o; o += align256(sizeof(cacfe::Stats));
+  off[2] = o; o += align256(n * sizeof(float));              // [T][K] copy for the column medians
+  off[3] = o; o += align256((size_t)K * sizeof(float));      // row medians
+  off[4] = o; o += align256((size_t)T * sizeof(float));      // column medians
+  off[5] = o; o += align256(n);                              // mask A
+  off[6] = o; o += align256(n);                              // mask B
+  off[7] = o; o += align256(n * sizeof(int));                // labels
+  off[8] = o; o += align256(n * sizeof(int));                // slot of every root
+  return o;
+}
+
+size_t cacfe_signal_workspace_bytes(int K, int T) {
+  if (K < 1 || T < 1) return 0;
+  size_t off[9];
+  return signal_layout(K, T, off);
+}
+
+int cacfe_signal_components(cacfe_plan* p, const float* spec, int K, int T, int open_size, int dil_h, int dil_w, int ero_h,
+                            int ero_w, unsigned char* mask_out, unsigned char* raw_mask_out, float* row_medians_out,
+                            float* col_medians_out, int32_t* comps_out, int max_components, int32_t* n_components_out, void* ws,
+                            void* stream) {
+  if (!p || !spec || !ws || !comps_out || !n_components_out) return fail(CACFE_EINVAL, "signal_components: null argument");
+  if (K < 1 || T < 1 || (long long)K * T > 2147483647LL) return fail(CACFE_ESHAPE, "signal_components: K=%d T=%d", K, T);
+  if (open_size < 1 || dil_h < 1 || dil_w < 1 || ero_h < 1 || ero_w < 1 || max_components < 1)
+    return fail(CACFE_EINVAL, "signal_components: structuring elements and max_components must be positive");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t off[9];
+  signal_layout(K, T, off);
+  char* w = (char*)ws;
+  const long long n = (long long)K * T;
+  cacfe::Stats* partial = (cacfe::Stats*)(w + off[0]);
+  cacfe::Stats* stats = (cacfe::Stats*)(w + off[1]);
+  float* spec_tk = (float*)(w + off[2]);
+  float* rm = (float*)(w + off[3]);
+  float* cm = (float*)(w + off[4]);
+  unsigned char* ma = (unsigned char*)(w + off[5]);
+  unsigned char* mb = (unsigned char*)(w + off[6]);
+  int* labels = (int*)(w + off[7]);
+  int* slot_of = (int*)(w + off[8]);
+  int launches = 0;
+  // a_max (identifytracks.py:79)
+  const int sblocks = (int)std::min<long long>(1024, (n + 4095) / 4096);
+  cacfe::stats_kernel<<<dim3(sblocks, 1), 256, 0, st>>>(spec, n, partial);
+  cacfe::stats_finalize_kernel<<<1, 32, 0, st>>>(partial, sblocks, stats);
+  // medians (:81-82): rows of [K][T]; columns = rows of the [T][K] copy
+  {
+    dim3 grid((T + cacfe::kTrTile - 1) / cacfe::kTrTile, (K + cacfe::kTrTile - 1) / cacfe::kTrTile, 1);
+    cacfe::spec_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(spec, spec_tk, K, T);   // in [K][T] -> out [T][K]
+  }
+  cacfe::select_median_kernel<<<K, 256, 0, st>>>(spec, T, stats, rm);
+  cacfe::select_median_kernel<<<T, 256, 0, st>>>(spec_tk, K, stats, cm);
+  const int eblocks = (int)std::min<long long>(8 * p->sm_count, (n + 255) / 256);
+  cacfe::signal_mask_kernel<<<eblocks, 256, 0, st>>>(spec, K, T, stats, rm, cm, ma);
+  launches += 6;
+  if (raw_mask_out) CUDA_TRY(cudaMemcpyAsync(raw_mask_out, ma, (size_t)n, cudaMemcpyDeviceToDevice, st));
+  if (row_medians_out) CUDA_TRY(cudaMemcpyAsync(row_medians_out, rm, (size_t)K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (col_medians_out) CUDA_TRY(cudaMemcpyAsync(col_medians_out, cm, (size_t)T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // morphology (:94-101): open, dilate, erode -- each a horizontal and a vertical pass
+  unsigned char *src = ma, *dst = mb;
+  auto pass = [&](bool is_max, int size, int horizontal) {
+    if (is_max)
+      cacfe::morph_pass_kernel<true><<<eblocks, 256, 0, st>>>(src, dst, K, T, size, size / 2, horizontal);
+    else
+      cacfe::morph_pass_kernel<false><<<eblocks, 256, 0, st>>>(src, dst, K, T, size, size / 2, horizontal);
+    std::swap(src, dst);
+    ++launches;
+  };
+  pass(false, open_size, 1);
+  pass(false, open_size, 0);
+  pass(true, open_size, 1);
+  pass(true, open_size, 0);
+  pass(true, dil_w, 1);
+  pass(true, dil_h, 0);
+  pass(false, ero_w, 1);
+  pass(false, ero_h, 0);
+  if (mask_out) CUDA_TRY(cudaMemcpyAsync(mask_out, src, (size_t)n, cudaMemcpyDeviceToDevice, st));
+  // connected components with stats (:106)
+  cacfe::Component* comps = reinterpret_cast<cacfe::Component*>(comps_out);
+  cacfe::ccl_clear_kernel<<<(max_components + 255) / 256, 256, 0, st>>>(comps, max_components, n_components_out);
+  cacfe::ccl_init_kernel<<<eblocks, 256, 0, st>>>(src, labels, n);
+  cacfe::ccl_merge_kernel<<<eblocks, 256, 0, st>>>(src, labels, K, T);
+  cacfe::ccl_flatten_kernel<<<eblocks, 256, 0, st>>>(labels, n, slot_of, n_components_out, max_components);
+  cacfe::ccl_stats_kernel<<<eblocks, 256, 0, st>>>(labels, K, T, slot_of, comps);
+  launches += 5;
+  return check_launch(p, "signal_components", launches);
 }
 
 int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float* out, long long entries,

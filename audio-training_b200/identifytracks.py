@@ -1,0 +1,119 @@
+"""Drop-in for the array part of the reference's `identifytracks` module:
+`signal_noise` (identifytracks.py:51-143) and `get_end` (:21-48) with the spectrogram, the medians, the morphology and
+the connected components on the GPU (cacfe_stft + cacfe_signal_components).  The object-level merging that follows
+(`merge_signals`, `get_tracks_from_signals`, :162-301) is small-N host logic and stays with the caller; pass
+`signal_class=identifytracks.Signal` to get the reference's own objects back.
+
+Bit-exactness: the integer stages (threshold mask -> open -> dilate -> erode -> components -> statistics) and the
+medians are exact against numpy / OpenCV on the same spectrogram.  The spectrogram itself is an FP32 FFT (librosa
+evaluates in float64 and rounds to complex64), so a pixel within ~1e-6 relative of its threshold can differ.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _runtime as rt
+
+SIGNAL_WIDTH = 0.25        # identifytracks.py:9
+TOP_FREQ = 48000 / 2
+
+
+def mel_freq(f):
+    return 2595.0 * np.log10(1.0 + f / 700.0)       # identifytracks.py:154-155
+
+
+class Signal:
+    """The five fields identifytracks.Signal is built from (:376-394) plus the derived mel range."""
+
+    def __init__(self, start, end, freq_start, freq_end, mass):
+        self.start, self.end, self.freq_start, self.freq_end, self.mass = start, end, freq_start, freq_end, mass
+        self.mel_freq_start, self.mel_freq_end = mel_freq(freq_start), mel_freq(freq_end)
+        self.predictions, self.track_id = [], None
+
+    def to_array(self):
+        return [self.start, self.end, self.freq_start, self.freq_end]
+
+    def __repr__(self):
+        return f"Signal: {self.start}-{self.end} f: {self.freq_start}-{self.freq_end} mass {self.mass}"
+
+
+def get_nfft(sr):
+    return int(math.pow(2, round(math.log2(sr // 10))))     # identifytracks.py:13-16
+
+
+def _bins(sr, n_fft):
+    """The loop over librosa.fft_frequencies of identifytracks.py:60-73 -> (freqs, lower_bin, upper_bin, height)."""
+    freqs = np.fft.rfftfreq(n_fft, 1.0 / sr)
+    lower_bin, upper_bin, height = None, 0, 0
+    for i, f in enumerate(freqs):
+        if f > 100 and lower_bin is None:
+            lower_bin = i - 1
+        if f > 20000:
+            upper_bin = i
+            break
+        if f > 100 and height == 0:
+            height = i + 1
+    return freqs, lower_bin, upper_bin, height
+
+
+def _spectrogram(frames, n_fft, hop_length, device):
+    """|librosa.stft(frames, n_fft, hop_length)| (centre framing, zero padding) of a whole recording -> CUDA [bins, T]."""
+    import torch
+    x = torch.as_tensor(np.asarray(frames, dtype=np.float32)) if not isinstance(frames, torch.Tensor) else frames
+    x = x.to(f"cuda:{device}", torch.float32).reshape(1, -1)
+    n = x.shape[1]
+    pad = (-n) % 4                                     # the streaming kernel copies 16-byte groups; zeros past the end are
+    if pad:                                            # what centre framing pads with anyway
+        x = torch.nn.functional.pad(x, (0, pad))
+    # one plan per recording length, not cached (get_plan's cache is for the fixed clip configurations)
+    plan = rt.Plan(rt.FrontendConfig(n_samples=n + pad, n_fft=n_fft, hop=hop_length, framing="center_zero", power=1,
+                                     channels=1, normalize=False), device)
+    spec = plan.stft(x)[0]
+    return spec[:, : 1 + n // hop_length].contiguous()
+
+
+def signal_noise(frames, sr, hop_length=281, n_fft=1024, min_width=None, min_height=None, signal_class=Signal, device=0,
+                 return_debug=False):
+    """identifytracks.signal_noise: -> (signals, og_spec).  As in the reference the `n_fft` argument is ignored
+    (`n_fft = 2048`, :55)."""
+    n_fft = 2048
+    spec = _spectrogram(frames, n_fft, hop_length, device)
+    freqs, _, _, height = _bins(sr, n_fft)
+    width = int(SIGNAL_WIDTH * sr / hop_length)
+    ero = (height // 10, width)
+    if ero[0] == 0 or ero[1] == 0:
+        ero = (3, 3)                                   # cv2.erode with an empty kernel (:101) uses the default 3 x 3 rectangle
+    plan = rt.get_plan(rt.FrontendConfig(), device)
+    out = plan.signal_components(spec, 4, (height, width), ero, debug=return_debug)
+    stats, debug = out if return_debug else (out, None)
+    stats = sorted(stats.tolist(), key=lambda s: s[0])  # stable, like the reference's sort by x (:110-111)
+    if min_height is None:
+        min_height = height - height // 10
+    if min_width is None:
+        min_width = 0.65 * width
+    stats = [s for s in stats if s[2] > min_width and s[3] > min_height]
+    signals = []
+    for s in stats:
+        max_freq = min(len(freqs) - 1, s[1] + s[3])
+        signals.append(signal_class(s[0] * 281 / sr, (s[0] + s[2]) * 281 / sr, freqs[s[1]], freqs[max_freq], s[4]))
+    og_spec = spec.cpu().numpy()
+    return (signals, og_spec, debug) if return_debug else (signals, og_spec)
+
+
+def get_end(frames, sr, device=0):
+    """identifytracks.get_end (:21-48): first second-long chunk of the 120-band mel image that is constant."""
+    from . import custommel
+    hop_length = 281
+    n_fft = get_nfft(sr)
+    spec = _spectrogram(frames, n_fft, hop_length, device)
+    mel = custommel.mel_spec(spec, sr, n_fft, hop_length, 120, 50, 11000, 1750, power=1).cpu().numpy()
+    start, chunk_length = 0, sr // hop_length
+    end = start + chunk_length
+    while end < mel.shape[1]:
+        data = mel[:, start:end]
+        if np.amax(data) == np.amin(data):
+            return start * hop_length // sr
+        start, end = end, end + chunk_length
+    return len(frames) / sr

@@ -170,6 +170,19 @@ int cacfe_pcen_backward(cacfe_plan* plan, const cacfe_pcen_params* params, const
                         float* grad_x_dev, float* grad_params_dev, int B, long long outer_per_clip, int T, int inner,
                         void* workspace_dev, void* stream);
 
+/* ---- identifytracks.signal_noise (identifytracks.py:51-143) from the magnitude spectrogram spec_dev[K][T]
+ * to the connected components of the signal mask: a_max, row / column medians, threshold (:79-91), open open_size x open_size,
+ * dilate dil_h x dil_w, erode ero_h x ero_w (:94-101; OpenCV conventions -- pass 3 x 3 where the reference hands cv2 an empty
+ * kernel), 8-connected components with statistics (:106).  Bit-exact against numpy / OpenCV on the same spectrogram.
+ * comps_dev: [max_components][6] int32 = (min_x, min_y, max_x, max_y, area, order_key); order_key reproduces OpenCV's label
+ * order; n_components_dev: one int32 (may exceed max_components: the list is then truncated).  Optional device outputs (may be
+ * NULL): final mask [K][T] uint8, thresholded mask before the morphology, row medians [K], column medians [T]. */
+size_t cacfe_signal_workspace_bytes(int K, int T);
+int cacfe_signal_components(cacfe_plan* plan, const float* spec_dev, int K, int T, int open_size, int dil_h, int dil_w, int ero_h,
+                            int ero_w, unsigned char* mask_dev, unsigned char* raw_mask_dev, float* row_medians_dev,
+                            float* col_medians_dev, int32_t* comps_dev, int max_components, int32_t* n_components_dev,
+                            void* workspace_dev, void* stream);
+
 /* ---- a12-a14: point-wise compression with a tensor- (entries = 1) or clip-wide (entries = B) statistic. */
 int cacfe_compress(cacfe_plan* plan, int mode, float param, const float* in_dev, float* out_dev, long long entries,
                    long long per_entry, void* workspace_dev, void* stream);

@@ -532,6 +532,72 @@ def synth_clips(indices, n=CLIP_SAMPLES, sr=SR, seed=20240):
     return out
 
 
+def synth_recording(seconds=12.0, sr=SR, seed=7):
+    """A whole recording for identifytracks.signal_noise: a noise floor plus band-limited bursts (0.4-1.5 s long,
+    0.4-2.5 kHz wide) so that the thresholded spectrogram has blobs on both sides of the width / height filter."""
+    rng = np.random.default_rng(seed)
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    x = 0.01 * rng.standard_normal(n)
+    for _ in range(int(seconds * 1.5)):
+        t0, dur = rng.uniform(0.2, seconds - 1.7), rng.uniform(0.1, 1.5)
+        f0, bw = rng.uniform(300, 9000), rng.uniform(100, 2500)
+        env = np.clip(1.0 - np.abs((t - t0 - dur / 2) / (dur / 2)) ** 4, 0.0, None)
+        fs = rng.uniform(f0, f0 + bw, 48)
+        ph = rng.uniform(0, 2 * np.pi, 48)
+        burst = np.sin(2 * np.pi * fs[:, None] * t[None, env > 0] + ph[:, None]).sum(0)
+        x[env > 0] += rng.uniform(0.02, 0.2) * env[env > 0] * burst / 7.0
+    return x.astype(np.float32)
+
+
+def signal_noise_arrays(spectogram, sr=SR, hop_length=HOP, n_fft=2048):
+    """identifytracks.signal_noise (identifytracks.py:51-143) from its spectrogram on, restated with numpy + OpenCV
+    (test infrastructure: cv2 is the reference's own dependency).  -> dict(mask, raw_mask, row_medians, column_medians,
+    stats [n, 5] in cv2 label order without the background row, height, width)."""
+    import cv2
+    freqs = np.fft.rfftfreq(n_fft, 1.0 / sr)                        # librosa.fft_frequencies (:59)
+    lower_bin, height = None, 0
+    for i, f in enumerate(freqs):                                   # :65-72
+        if f > 100 and lower_bin is None:
+            lower_bin = i - 1
+        if f > 20000:
+            break
+        if f > 100 and height == 0:
+            height = i + 1
+    spectogram = np.asarray(spectogram, dtype=np.float32)
+    a_max = np.amax(spectogram)
+    spectogram = spectogram / a_max                                 # :79-80
+    row_medians = np.median(spectogram, axis=1)                     # :81-82
+    column_medians = np.median(spectogram, axis=0)
+    signal = (spectogram > 2 * column_medians[np.newaxis, :]) & (spectogram > 3 * row_medians[:, np.newaxis])   # :91
+    raw = signal.astype(np.uint8)
+    signal = cv2.morphologyEx(raw, cv2.MORPH_OPEN, np.ones((4, 4), np.uint8))                                     # :94
+    width = int(0.25 * sr / hop_length)                                                                             # :96-97
+    signal = cv2.dilate(signal, np.ones((height, width), np.uint8))                                                 # :100
+    signal = cv2.erode(signal, np.ones((height // 10, width), np.uint8))                                            # :101
+    _, _, stats, _ = cv2.connectedComponentsWithStats(signal)                                                       # :106
+    return {"mask": signal, "raw_mask": raw, "row_medians": row_medians, "column_medians": column_medians,
+            "stats": stats[1:].astype(np.int32), "height": height, "width": width, "freqs": freqs}
+
+
+def signal_noise(frames, sr=SR, hop_length=HOP, min_width=None, min_height=None):
+    """identifytracks.signal_noise end to end -> ([start, end, freq_start, freq_end, mass] rows, og_spec)."""
+    spec = np.abs(stft_librosa(np.asarray(frames, dtype=np.float32), 2048, hop_length).astype(np.complex64))   # :56
+    r = signal_noise_arrays(spec, sr, hop_length)
+    stats = sorted(r["stats"].tolist(), key=lambda s: s[0])                                                        # :110-111
+    height, width, freqs = r["height"], r["width"], r["freqs"]
+    if min_height is None:
+        min_height = height - height // 10
+    if min_width is None:
+        min_width = 0.65 * width
+    stats = [s for s in stats if s[2] > min_width and s[3] > min_height]                                           # :128
+    out = []
+    for s in stats:                                                                                                # :136-142
+        max_freq = min(len(freqs) - 1, s[1] + s[3])
+        out.append([s[0] * 281 / sr, (s[0] + s[2]) * 281 / sr, freqs[s[1]], freqs[max_freq], s[4]])
+    return np.array(out, dtype=np.float64).reshape(-1, 5), spec
+
+
 def within_tolerance(ours, truth, rel=REL_TOL, abs_=ABS_TOL):
     """North-star acceptance: |ours - truth| <= rel*|truth| + abs.  Returns (ok, worst_ratio)."""
     ours = np.asarray(ours, dtype=np.float64)

@@ -530,3 +530,63 @@ def test_pcen_trainable_module(oracle):
     got = [float(layer.gain.grad), float(layer.bias.grad), float(layer.root.grad), float(layer.smooth.grad)]
     assert np.allclose(got, want_dp, rtol=5e-4, atol=1e-4 * np.abs(want_dp).max())
     assert layer.a_power.grad is None                                    # declared, never used (Q12)
+
+
+# ------------------------------------------------------------------------------------------------ signal_noise (8f rank 3)
+def test_signal_components_bit_exact(oracle):
+    """cacfe_signal_components on the oracle's own f32 spectrogram: medians, thresholded mask, morphology, components and
+    their statistics are integer / order-statistic work -- bit-exact against numpy + OpenCV."""
+    for seconds, seed in ((12.0, 7), (7.5, 11), (3.3, 5)):             # 2050 (even), 1282 (even), 564 (even) ... frames
+        frames = oracle.synth_recording(seconds, seed=seed)
+        spec = np.abs(oracle.stft_librosa(frames, 2048, 281).astype(np.complex64))
+        if seed == 5:
+            spec = np.ascontiguousarray(spec[:, :563])                 # an odd frame count: single middle element
+        want = oracle.signal_noise_arrays(spec)
+        plan = rt.get_plan(rt.FrontendConfig(), 0)
+        stats, dbg = plan.signal_components(torch.from_numpy(spec).cuda(), 4, (want["height"], want["width"]), (3, 3), debug=True)
+        assert np.array_equal(dbg["row_medians"].cpu().numpy(), want["row_medians"])
+        assert np.array_equal(dbg["column_medians"].cpu().numpy(), want["column_medians"])
+        assert np.array_equal(dbg["raw_mask"].cpu().numpy(), want["raw_mask"])
+        assert np.array_equal(dbg["mask"].cpu().numpy(), want["mask"])
+        assert len(want["stats"]) >= 3
+        assert np.array_equal(stats, want["stats"])                    # same components, same statistics, OpenCV's label order
+
+
+def test_signal_components_random_masks(oracle):
+    """Morphology + components on a spectrogram built to give a busy, random mask (many small blobs, ties in x)."""
+    import cv2
+    rng = np.random.default_rng(3)
+    seeds = cv2.dilate((rng.random((257, 900)) < 0.012).astype(np.uint8), np.ones((3, 4), np.uint8))   # ~8 % foreground blobs
+    spec = (1.0 + 0.01 * rng.random((257, 900)) + 9.0 * seeds).astype(np.float32)                      # medians ~1, blobs ~10
+    want_raw = oracle.signal_noise_arrays(spec)["raw_mask"]
+    assert np.array_equal(want_raw, seeds)
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    for open_size, dil, ero in ((1, (1, 1), (1, 1)), (2, (3, 5), (3, 3)), (1, (2, 7), (1, 4))):
+        stats, dbg = plan.signal_components(torch.from_numpy(spec).cuda(), open_size, dil, ero, debug=True)
+        m = cv2.morphologyEx(want_raw, cv2.MORPH_OPEN, np.ones((open_size, open_size), np.uint8))
+        m = cv2.erode(cv2.dilate(m, np.ones(dil, np.uint8)), np.ones(ero, np.uint8))
+        assert np.array_equal(dbg["mask"].cpu().numpy(), m)
+        _, _, want, _ = cv2.connectedComponentsWithStats(m)
+        assert len(want) > 40 and np.array_equal(stats, want[1:])
+
+
+def test_signal_noise_end_to_end(oracle):
+    """identifytracks.signal_noise on the device (FP32 STFT of the whole recording included) against the signals the
+    reference's own function produced.  The FFT precision differs (librosa: float64 rounded to complex64), so a pixel
+    within ~1e-6 of its threshold may flip: boxes must agree to within one frame / bin and 1 % of the mass."""
+    from audio_training_b200 import identifytracks as it
+    g = np.load(os.path.join(GOLDEN, "signal_noise.npz"))
+    for tag in ("a", "b"):
+        seconds, seed = g[f"params_{tag}"]
+        frames = oracle.synth_recording(float(seconds), seed=int(seed))
+        signals, og_spec = it.signal_noise(frames, 48000)
+        want = g[f"signals_{tag}"]
+        assert og_spec.shape == tuple(g[f"spec_shape_{tag}"])
+        ref_spec = np.abs(oracle.stft_librosa(frames, 2048, 281))
+        assert np.all(np.abs(og_spec - ref_spec) <= 1e-4 * ref_spec + 2e-6 * ref_spec.max(axis=0, keepdims=True))
+        got = np.array([[s.start, s.end, s.freq_start, s.freq_end, s.mass] for s in signals])
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.all(np.abs(got[:, :2] - want[:, :2]) <= 281 / 48000 + 1e-9)
+        assert np.all(np.abs(got[:, 2:4] - want[:, 2:4]) <= 48000 / 2048 + 1e-9)
+        assert np.all(np.abs(got[:, 4] - want[:, 4]) <= 0.01 * want[:, 4] + 2)
+    assert it.get_end(oracle.synth_recording(4.0, seed=2), 48000) == 4.0

@@ -299,3 +299,19 @@ def test_pcen_backward_oracle_against_finite_differences(oracle):
         assert abs((f(xp) - f(xm)) / (2 * h) - dx[idx]) <= 1e-5 * max(1.0, abs(dx[idx]))
     _, clipped = oracle.pcen_backward(x, g, gain=1.2, root=0.8, smooth=1.5, scope="none")
     assert clipped[0] == 0 and clipped[2] == 0 and clipped[3] == 0       # (and root clipped to 1 removes the bias term too)
+
+
+def test_signal_noise_oracle_against_reference_golden(oracle):
+    """oracle.signal_noise (numpy + OpenCV restatement) against tests/golden/signal_noise.npz, which the reference's own
+    identifytracks.signal_noise produced (oracle/ref_shim/gen_signal_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "signal_noise.npz"))
+    for tag in ("a", "b"):
+        seconds, seed = g[f"params_{tag}"]
+        frames = oracle.synth_recording(float(seconds), seed=int(seed))
+        sig, spec = oracle.signal_noise(frames)
+        assert tuple(g[f"spec_shape_{tag}"]) == spec.shape
+        assert np.isclose(float(spec.astype(np.float64).sum()), float(g[f"spec_sum_{tag}"][0]), rtol=1e-9)
+        assert sig.shape == g[f"signals_{tag}"].shape and len(sig) >= 8
+        assert np.array_equal(sig, g[f"signals_{tag}"])
