@@ -1109,7 +1109,7 @@ int cacfe_signal_components(cacfe_plan* p, const float* spec, int K, int T, int 
   // connected components with stats (:106)
   cacfe::Component* comps = reinterpret_cast<cacfe::Component*>(comps_out);
   cacfe::ccl_clear_kernel<<<(max_components + 255) / 256, 256, 0, st>>>(comps, max_components, n_components_out);
-  cacfe::ccl_init_kernel<<<eblocks, 256, 0, st>>>(src, labels, n);
+  cacfe::ccl_init_kernel<<<eblocks, 256, 0, st>>>(src, labels, K, T);
   cacfe::ccl_merge_kernel<<<eblocks, 256, 0, st>>>(src, labels, K, T);
   cacfe::ccl_flatten_kernel<<<eblocks, 256, 0, st>>>(labels, n, slot_of, n_components_out, max_components);
   cacfe::ccl_stats_kernel<<<eblocks, 256, 0, st>>>(labels, K, T, slot_of, comps);

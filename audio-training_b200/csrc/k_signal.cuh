@@ -172,21 +172,52 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const unsigned char* __restrict__ mask, int* __restrict__ L, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    L[i] = mask[i] ? (int)i : -1;
+// Initial labels: every foreground pixel points at the first pixel of its horizontal run inside the warp's 32 consecutive
+// pixels (ballot + bit scan).  A run that continues from the previous warp is joined by one union in ccl_merge_kernel.
+// Both kernels walk the image with the same warp <-> pixel map (grid-stride in multiples of the block size).
+__device__ __forceinline__ bool ccl_left_link(const unsigned char* mask, long long i, long long n, int W, bool& fg, int& x, int& y) {
+  fg = i < n && mask[i] != 0;
+  y = (int)(i / W);
+  x = (int)(i - (long long)y * W);
+  return fg && x > 0 && mask[i - 1] != 0;
 }
+__global__ void __launch_bounds__(256) ccl_init_kernel(const unsigned char* __restrict__ mask, int* __restrict__ L, int H, int W) {
+  const long long n = (long long)H * W, span = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += span) {
+    const long long i = i0 + threadIdx.x;
+    bool fg;
+    int x, y;
+    const bool link = ccl_left_link(mask, i, n, W, fg, x, y);
+    const unsigned links = __ballot_sync(kFullMask, link);
+    if (i < n) {
+      const unsigned starts = ~links & ((2u << lane) - 1u);           // lanes <= this one that begin a run (or are background)
+      const int first = starts ? 31 - __clz(starts) : 0;
+      L[i] = fg ? (int)(i - (lane - first)) : -1;
+    }
+  }
+}
+// Unions across rows, pruned to the places where a run meets something new in the row above: with u / ul / ur the pixels
+// above, above-left and above-right,  (i, u) unless the left neighbour already joined ul (ul and u are neighbours in their
+// own row);  if u is background: (i, ul) unless the left neighbour -- whose u that is -- exists, and (i, ur).
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const unsigned char* __restrict__ mask, int* __restrict__ L, int H, int W) {
-  const long long n = (long long)H * W;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (!mask[i]) continue;
-    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
-    if (x > 0 && mask[i - 1]) ccl_union(L, (int)i, (int)i - 1);
-    if (y > 0) {
-      const long long up = i - W;
-      if (mask[up]) ccl_union(L, (int)i, (int)up);
-      if (x > 0 && mask[up - 1]) ccl_union(L, (int)i, (int)up - 1);
-      if (x + 1 < W && mask[up + 1]) ccl_union(L, (int)i, (int)up + 1);
+  const long long n = (long long)H * W, span = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += span) {
+    const long long i = i0 + threadIdx.x;
+    bool fg;
+    int x, y;
+    const bool left = ccl_left_link(mask, i, n, W, fg, x, y);
+    if (!fg) continue;
+    if (lane == 0 && left) ccl_union(L, (int)i, (int)i - 1);          // the run continues from the previous warp
+    if (y == 0) continue;
+    const long long up = i - W;
+    const bool u = mask[up] != 0, ul = x > 0 && mask[up - 1] != 0, ur = x + 1 < W && mask[up + 1] != 0;
+    if (u) {
+      if (!(left && ul)) ccl_union(L, (int)i, (int)up);
+    } else {
+      if (ul && !left) ccl_union(L, (int)i, (int)up - 1);
+      if (ur) ccl_union(L, (int)i, (int)up + 1);
     }
   }
 }

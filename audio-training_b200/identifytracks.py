@@ -58,28 +58,38 @@ def _bins(sr, n_fft):
     return freqs, lower_bin, upper_bin, height
 
 
-def _spectrogram(frames, n_fft, hop_length, device):
-    """|librosa.stft(frames, n_fft, hop_length)| (centre framing, zero padding) of a whole recording -> CUDA [bins, T]."""
+_plans = {}   # (padded length, n_fft, hop, device) -> Plan; a handful of recording lengths, oldest dropped first
+
+
+def _spectrogram(x, n_fft, hop_length):
+    """|librosa.stft(frames, n_fft, hop_length)| (centre framing, zero padding) of a whole recording, CUDA [n] -> [bins, T]."""
     import torch
-    x = torch.as_tensor(np.asarray(frames, dtype=np.float32)) if not isinstance(frames, torch.Tensor) else frames
-    x = x.to(f"cuda:{device}", torch.float32).reshape(1, -1)
+    x = x.reshape(1, -1)
     n = x.shape[1]
     pad = (-n) % 4                                     # the streaming kernel copies 16-byte groups; zeros past the end are
     if pad:                                            # what centre framing pads with anyway
         x = torch.nn.functional.pad(x, (0, pad))
-    # one plan per recording length, not cached (get_plan's cache is for the fixed clip configurations)
-    plan = rt.Plan(rt.FrontendConfig(n_samples=n + pad, n_fft=n_fft, hop=hop_length, framing="center_zero", power=1,
-                                     channels=1, normalize=False), device)
+    key = (n + pad, n_fft, hop_length, x.device.index)
+    plan = _plans.pop(key, None)
+    if plan is None:
+        plan = rt.Plan(rt.FrontendConfig(n_samples=n + pad, n_fft=n_fft, hop=hop_length, framing="center_zero", power=1,
+                                         channels=1, normalize=False), x.device.index)
+    _plans[key] = plan
+    while len(_plans) > 4:
+        _plans.pop(next(iter(_plans)))
     spec = plan.stft(x)[0]
-    return spec[:, : 1 + n // hop_length].contiguous()
+    t = 1 + n // hop_length
+    return spec if spec.shape[1] == t else spec[:, :t].contiguous()
 
 
-def signal_noise(frames, sr, hop_length=281, n_fft=1024, min_width=None, min_height=None, signal_class=Signal, device=0,
+def signal_noise(frames, sr, hop_length=281, n_fft=1024, min_width=None, min_height=None, signal_class=Signal,
                  return_debug=False):
     """identifytracks.signal_noise: -> (signals, og_spec).  As in the reference the `n_fft` argument is ignored
-    (`n_fft = 2048`, :55)."""
+    (`n_fft = 2048`, :55).  og_spec comes back in the flavour of `frames` (numpy in, numpy out; CUDA tensor in, CUDA out)."""
     n_fft = 2048
-    spec = _spectrogram(frames, n_fft, hop_length, device)
+    x, restore = rt.to_device(frames)
+    device = x.device.index
+    spec = _spectrogram(x, n_fft, hop_length)
     freqs, _, _, height = _bins(sr, n_fft)
     width = int(SIGNAL_WIDTH * sr / hop_length)
     ero = (height // 10, width)
@@ -98,16 +108,17 @@ def signal_noise(frames, sr, hop_length=281, n_fft=1024, min_width=None, min_hei
     for s in stats:
         max_freq = min(len(freqs) - 1, s[1] + s[3])
         signals.append(signal_class(s[0] * 281 / sr, (s[0] + s[2]) * 281 / sr, freqs[s[1]], freqs[max_freq], s[4]))
-    og_spec = spec.cpu().numpy()
+    og_spec = restore(spec)
     return (signals, og_spec, debug) if return_debug else (signals, og_spec)
 
 
-def get_end(frames, sr, device=0):
+def get_end(frames, sr):
     """identifytracks.get_end (:21-48): first second-long chunk of the 120-band mel image that is constant."""
     from . import custommel
     hop_length = 281
     n_fft = get_nfft(sr)
-    spec = _spectrogram(frames, n_fft, hop_length, device)
+    x, _ = rt.to_device(frames)
+    spec = _spectrogram(x, n_fft, hop_length)
     mel = custommel.mel_spec(spec, sr, n_fft, hop_length, 120, 50, 11000, 1750, power=1).cpu().numpy()
     start, chunk_length = 0, sr // hop_length
     end = start + chunk_length

@@ -21,7 +21,7 @@ for _ in range(n):
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / n * 1e3
 # the array part alone, device resident
-d = it._spectrogram(x, 2048, 281, 0)
+d = it._spectrogram(x, 2048, 281)
 plan = rt.get_plan(rt.FrontendConfig(), 0)
 for _ in range(2):
     plan.signal_components(d, 4, (6, 42), (3, 3))
