@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""identifytracks.signal_noise on one recording: device path (FP32 STFT + cacfe_signal_components) against the numpy +
+"""(Lives under tests/ because it times the oracle next to the device path.)  identifytracks.signal_noise on one recording: device path (FP32 STFT + cacfe_signal_components) against the numpy +
 OpenCV restatement on the host cores.  CUDA-event timed after warm-up; prints one JSON line.
-    python tools/bench_signal.py [seconds]"""
+    python tests/bench_signal.py [seconds]"""
 import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
