@@ -18,6 +18,7 @@
 #include "k_frontend.cuh"
 #include "k_frontend_v3.cuh"
 #include "k_melspec.cuh"
+#include "k_normalize_cluster.cuh"
 #include "k_melspec_stream.cuh"
 #include "k_melspec_tc.cuh"
 #include "k_pcen.cuh"
@@ -420,6 +421,8 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
     e = upload((void**)&p->d_tc_chunks, p->tc_chunks.data(), p->tc_chunks.size() * sizeof(cacfe::MelTcChunk));
   if (e == cudaSuccess && p->tc_ok)
     e = cudaFuncSetAttribute(cacfe::melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kTcSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cacfe::row_normalize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kNcMaxBytesPerCta);
   if (e == cudaSuccess && p->ms_ok) e = upload((void**)&p->d_ms_rows, ms_rows.data(), ms_rows.size() * sizeof(float4));
   if (e == cudaSuccess && p->ms_ok) {
     const void* kernels[24] = {
@@ -617,6 +620,14 @@ int cacfe_normalize(cacfe_plan* p, const float* in, float* out, long long rows, 
   if (rows < 1 || n < 1 || rows > 65535) return fail(CACFE_ESHAPE, "normalize: rows=%lld n=%lld", rows, n);
   CUDA_TRY(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
+  // a cluster of 8 CTAs holds the clip in (distributed) shared memory between the min/max and the rescale: one HBM read
+  const long long per_cta = n / cacfe::kNcCluster;
+  if (!p->force_generic && n % (4 * cacfe::kNcCluster) == 0 && per_cta * 4 <= cacfe::kNcMaxBytesPerCta &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && rows * cacfe::kNcCluster <= 2147483647LL) {
+    cacfe::row_normalize_cluster_kernel<<<(unsigned)(rows * cacfe::kNcCluster), cacfe::kNcThreads, (size_t)per_cta * 4, st>>>(
+        in, out, n, (int)per_cta);
+    return check_launch(p, "normalize (cluster)", 1);
+  }
   int splits = pick_splits(p, rows);
   if (rows * splits * (long long)sizeof(float2) > (long long)frontend_ws_bytes((int)rows)) splits = 1;
   float2* partial = (float2*)ws;

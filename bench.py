@@ -303,6 +303,46 @@ def run_ours(args):
                "checksum": float(h_out[0][0, :4, :4].sum())}
         del pipes, h_in, h_out
 
+    # ---- the other HBM-bound rows of the path, timed alone on rank 0: not part of `value` ----------------
+    rows = None
+    if rank == 0 and world == 1 and not args.no_rows:
+        def alone(fn, n=10):
+            for _ in range(2):
+                fn()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+
+        def row(ms, clips, alg_bytes_per_clip, moved_bytes_per_clip):
+            return {"ms": ms, "clips": clips, "clips_per_s": clips / ms * 1e3,
+                    "algorithmic_GBps": clips * alg_bytes_per_clip / ms / 1e6,
+                    "frac_of_hbm": clips * alg_bytes_per_clip / ms / 1e6 / peaks["hbm_gbs"],
+                    "moved_GBps": clips * moved_bytes_per_clip / ms / 1e6}
+
+        T, M = plan.n_frames, cfg.n_mels
+        feat = T * M * 4
+        mel = plan.frontend(x)
+        rows = {"note": "standalone entry points, CUDA events, inputs resident and larger than L2; algorithmic bytes per clip as in "
+                        "SURVEY 8d, moved = what the implementation has to touch (a tensor-global statistic costs one more read)"}
+        rows["pcen_tensor_scope"] = row(alone(lambda: plan.pcen(mel, params)), B, 2 * feat, 3 * feat)
+        rows["pcen_no_minmax"] = row(alone(lambda: plan.pcen(mel, rt.pcen_params(norm_scope="none"))), B, 2 * feat, 2 * feat)
+        rows["ema"] = row(alone(lambda: plan.ema(mel, 0.04)), B, 2 * feat, 2 * feat)
+        rows["normalize"] = row(alone(lambda: plan.normalize(x)), B, 2 * CLIP * 4, 3 * CLIP * 4)
+        rows["minmax_epilogue"] = row(alone(lambda: plan.compress(mel, "minmax")), B, 2 * feat, 3 * feat)
+        del mel
+        nb = min(B, 384)
+        pc = rt.get_plan(rt.FrontendConfig(power=1, channels=1), local)
+        spec = torch.rand((nb, pc.n_bins, T), device=device)
+        lo, hi = pc.bin_range()
+        alg = (hi - lo + 1) * T * 4 + M * T * 4
+        rows["mel_from_spectrogram"] = row(alone(lambda: pc.mel_from_spectrogram(spec)), nb, alg, alg)
+        del spec
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, nb = cpu_reference_run(32, budget_s=15.0)
@@ -316,7 +356,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD.format(B=B),
                            "batch_per_gpu": B, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (B * CLIP * 4 / 1e9),
                            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "other_rows": rows, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "checksum": float(out[0, :4, :4].sum())}
         print(json.dumps(line))
     if world > 1:
@@ -334,6 +374,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-rows", action="store_true", help="skip the standalone timing of the other HBM-bound rows")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -54,6 +54,24 @@ def test_normalize_bit_exact(oracle, golden, clips):
     assert np.array_equal(atb.normalize_data(ragged), oracle.normalize(ragged, np.float32))
 
 
+def test_normalize_cluster_kernel(oracle, clips):
+    """row_normalize_cluster_kernel (a cluster of 8 CTAs keeps the clip in distributed shared memory between the min/max and
+    the rescale) against the two-kernel path and the oracle: bit-identical."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([clips, rng.standard_normal((5, 144000)).astype(np.float32) * 3 + 7,
+                        np.full((1, 144000), 0.25, np.float32)])                      # the last clip is constant: NaN (Q1)
+    t = torch.from_numpy(x).cuda()
+    plan = rt.Plan(rt.FrontendConfig(), 0)
+    a = plan.normalize(t)
+    plan.force_generic(True)
+    b = plan.normalize(t)
+    assert torch.equal(a[:-1], b[:-1]) and torch.isnan(a[-1]).all() and torch.isnan(b[-1]).all()
+    assert np.array_equal(a[:-1].cpu().numpy(), oracle.normalize(x[:-1], np.float32))
+    for n in (32, 4000, 8 * 51200):                                                    # smallest, odd multiple, largest that fits
+        y = torch.from_numpy(rng.standard_normal((3, n)).astype(np.float32)).cuda()
+        assert np.array_equal(rt.Plan(rt.FrontendConfig(), 0).normalize(y).cpu().numpy(), oracle.normalize(y.cpu().numpy(), np.float32))
+
+
 # ------------------------------------------------------------------------------------------------ path A
 def test_path_a_vs_golden_and_oracle(oracle, golden, xn, bank):
     out, _ = atb.raw_to_mel(xn, None)

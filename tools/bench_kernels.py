@@ -31,7 +31,7 @@ def report(op, ms, bytes_, units, unit_name="clips"):
 
 x = torch.rand((B, N), device="cuda") - 0.5
 plan = rt.Plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
-report("normalize (K0 + row_normalize)", timed(lambda: plan.normalize(x)), B * N * 4 * 3, B)
+report("normalize (cluster of 8 CTAs, clip in DSMEM)", timed(lambda: plan.normalize(x)), B * N * 4 * 2, B)
 report("frontend raw -> mel [B,T,M] (K0 + K1)", timed(lambda: plan.frontend(x)), B * (N * 4 + T * M * 4), B)
 img = rt.Plan(rt.FrontendConfig(normalize=True, channels=3, out_layout="bmtc"), 0)
 report("frontend raw -> image [B,M,T,3] (raw_to_mel)", timed(lambda: img.frontend(x)), B * (N * 4 + 3 * T * M * 4), B)
