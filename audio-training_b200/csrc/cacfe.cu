@@ -422,6 +422,9 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->tc_ok)
     e = cudaFuncSetAttribute(cacfe::melspec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kTcSmemBytes);
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cacfe::pcen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             cacfe::kBwdMaxSeg * cacfe::kBwdMaxThreads * (int)sizeof(float));
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(cacfe::row_normalize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cacfe::kNcMaxBytesPerCta);
   if (e == cudaSuccess && p->ms_ok) e = upload((void**)&p->d_ms_rows, ms_rows.data(), ms_rows.size() * sizeof(float4));
   if (e == cudaSuccess && p->ms_ok) {
@@ -967,9 +970,18 @@ int cacfe_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* in, float
 }
 
 // ---- PCEN backward -----------------------------------------------------------------------------
+// lanes of a clip spread evenly over as few blocks of at most kBwdMaxThreads as it takes (160 mel lanes -> one block of 160)
+static PcenGrid pcen_bwd_grid(long long rows_per_clip) {
+  PcenGrid g;
+  g.gx = (int)((rows_per_clip + cacfe::kBwdMaxThreads - 1) / cacfe::kBwdMaxThreads);
+  const long long per = (rows_per_clip + g.gx - 1) / g.gx;
+  g.block = (int)(((per + 31) / 32) * 32);
+  return g;
+}
+
 static size_t pcen_bwd_layout(int B, long long rows_per_clip, size_t off[4]) {
   const PcenGrid g = pcen_grid(rows_per_clip);
-  const int gx2 = (int)((rows_per_clip + cacfe::kBwdThreads - 1) / cacfe::kBwdThreads);
+  const int gx2 = pcen_bwd_grid(rows_per_clip).gx;
   const int gmax = g.gx > gx2 ? g.gx : gx2;
   size_t o = 0;
   off[0] = o; o += align256((size_t)B * g.gx * sizeof(float2));          // forward block extremes
@@ -1029,8 +1041,10 @@ int cacfe_pcen_backward(cacfe_plan* p, const cacfe_pcen_params* q, const float* 
     cacfe::pcen_bwd_fold_kernel<<<entries, 32, 0, st>>>(partial, per_entry, extremes, fold);
     launches += 4;
   }
-  const int gx2 = (int)((a.f.rows_per_clip + cacfe::kBwdThreads - 1) / cacfe::kBwdThreads);
-  cacfe::pcen_bwd_kernel<<<dim3(gx2, B), cacfe::kBwdThreads, 0, st>>>(a);
+  const PcenGrid g2 = pcen_bwd_grid(a.f.rows_per_clip);
+  const int gx2 = g2.gx;
+  const size_t ck = (size_t)((T + cacfe::kBwdSeg - 1) / cacfe::kBwdSeg) * g2.block * sizeof(float);
+  cacfe::pcen_bwd_kernel<<<dim3(gx2, B), g2.block, ck, st>>>(a);
   cacfe::pcen_bwd_params_kernel<<<1, 32, 0, st>>>(partial, B * gx2, q->gain, q->root, q->smooth, grad_params);
   return check_launch(p, "pcen_backward", launches);
 }

@@ -15,19 +15,20 @@
 //                            accumulates per block  sum G, sum G p, #(p == mn), #(p == mx)          reads x, G
 //   pcen_bwd_fold_kernel     folds the partials into  2/R, dL/dmx / n_max, dL/dmn / n_min           tiny
 //   pcen_bwd_kernel          reverse sweep.  M_t cannot be run backwards stably (division by 1 - w per step), so a
-//                            first forward walk keeps the state entering every 32-step segment in shared memory; each
+//                            first forward walk keeps the state entering every 16-step segment in shared memory; each
 //                            segment is then replayed forward into registers and differentiated backwards.  Scalar
 //                            gradients: per-thread float sums, block-reduced in double.            reads x (x2), G; writes dx
-// T <= 32 * kBwdMaxSeg.
+// T <= kBwdSeg * kBwdMaxSeg.
 #pragma once
 #include "k_pcen.cuh"
 
 namespace cacfe {
 
 constexpr int kScopeClip = 1, kScopeNone = 2;   // cacfe_norm_scope (include/cacfe.h)
-constexpr int kBwdSeg = 32;
-constexpr int kBwdMaxSeg = 64;      // T <= 2048
-constexpr int kBwdThreads = 128;    // kBwdMaxSeg * kBwdThreads floats of checkpoints = 32 KB
+constexpr int kBwdSeg = 16;         // time steps per replayed segment (the unrolled reverse loop: 16 x ~150 instructions; 32
+                                    // steps did not fit the instruction cache: 1.8 of 9 stall cycles per issue were fetches)
+constexpr int kBwdMaxSeg = 128;     // T <= 2048
+constexpr int kBwdMaxThreads = 192; // checkpoints: n_seg * blockDim floats of dynamic shared memory
 
 struct PcenBwdArgs {
   PcenArgs f;                  // forward constants; f.in = x, f.out unused
@@ -79,15 +80,26 @@ __global__ void __launch_bounds__(256) pcen_bwd_reduce_kernel(const PcenBwdArgs 
     const float* x = f.in + base;
     const float* g = a.g + base;
     float m = x[0];
-    for (int t = 0; t < f.T; ++t) {
-      const float v = ld_stream(x + (size_t)t * f.inner), gv = ld_stream(g + (size_t)t * f.inner);
+    auto take = [&](float v, float gv) {
       m = __fadd_rn(__fmul_rn(f.w, v), __fmul_rn(f.one_minus_w, m));
       const float p = pcen_point(v, m, f);
       s0 += gv;
       s1 = fmaf(gv, p - e.x, s1);
       n_mn += p == e.x ? 1.0f : 0.0f;
       n_mx += p == e.y ? 1.0f : 0.0f;
+    };
+    int t = 0;
+    for (; t + 8 <= f.T; t += 8) {   // 16 loads in flight per thread
+      float v[8], gv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = ld_stream(x + (size_t)(t + u) * f.inner);
+        gv[u] = ld_stream(g + (size_t)(t + u) * f.inner);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) take(v[u], gv[u]);
     }
+    for (; t < f.T; ++t) take(ld_stream(x + (size_t)t * f.inner), ld_stream(g + (size_t)t * f.inner));
   }
   double* out = a.partial + ((size_t)clip * gridDim.x + blockIdx.x) * 4;
   const double t0 = block_sum_d(s0, scratch), t1 = block_sum_d(s1, scratch), t2 = block_sum_d(n_mn, scratch),
@@ -118,8 +130,8 @@ __global__ void pcen_bwd_fold_kernel(const double* __restrict__ partial, int per
   fold[blockIdx.x] = make_float4((float)(2.0 / R), (float)(dmx / fmax(n_mx, 1.0)), (float)(dmn / fmax(n_mn, 1.0)), 0.0f);
 }
 
-__global__ void __launch_bounds__(kBwdThreads) pcen_bwd_kernel(const PcenBwdArgs a) {
-  __shared__ float ckpt[kBwdMaxSeg][kBwdThreads];
+__global__ void __launch_bounds__(kBwdMaxThreads) pcen_bwd_kernel(const PcenBwdArgs a) {
+  extern __shared__ float ckpt[];     // [n_seg][blockDim.x]
   __shared__ double scratch[8];
   const PcenArgs& f = a.f;
   const int clip = blockIdx.y;
@@ -144,28 +156,38 @@ __global__ void __launch_bounds__(kBwdThreads) pcen_bwd_kernel(const PcenBwdArgs
     }
     const float ln2 = 0.6931471805599453f;
     const float ln_b = __logf(f.bias);
+    const float dpdb = f.inv_root * f.bias_pow / f.bias;   // d(b^(1/r))/db
     const int n_seg = (f.T + kBwdSeg - 1) / kBwdSeg;
     // ---- forward walk: the smoother state entering every segment ----------------------------------------------------
     {
       float m = x[0];
       for (int s = 0; s < n_seg; ++s) {
-        ckpt[s][threadIdx.x] = m;
-        const int t1 = min(f.T, (s + 1) * kBwdSeg);
-        for (int t = s * kBwdSeg; t < t1; ++t)
-          m = __fadd_rn(__fmul_rn(f.w, ld_stream(x + (size_t)t * f.inner)), __fmul_rn(f.one_minus_w, m));
+        ckpt[s * blockDim.x + threadIdx.x] = m;
+        float v[kBwdSeg];   // the segment's loads are all issued before the (sequential) fold
+#pragma unroll
+        for (int u = 0; u < kBwdSeg; ++u) v[u] = s * kBwdSeg + u < f.T ? x[(size_t)(s * kBwdSeg + u) * f.inner] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < kBwdSeg; ++u) m = __fadd_rn(__fmul_rn(f.w, v[u]), __fmul_rn(f.one_minus_w, m));   // steps past T only follow the last checkpoint
       }
     }
     // ---- reverse sweep, one segment at a time -----------------------------------------------------------------------
     float lam = 0.0f;   // l_{t+1}
     for (int s = n_seg - 1; s >= 0; --s) {
       const int t_lo = s * kBwdSeg;
-      const float m_in = ckpt[s][threadIdx.x];
-      float xv[kBwdSeg], mv[kBwdSeg];
+      const float m_in = ckpt[s * blockDim.x + threadIdx.x];
+      // x and dL/dout of the whole segment are loaded up front: inside the reverse loop every load would queue behind the
+      // previous step's dx store (the compiler must assume they alias) and expose one memory latency per time step
+      float xv[kBwdSeg], mv[kBwdSeg], gvv[kBwdSeg];
+#pragma unroll
+      for (int u = 0; u < kBwdSeg; ++u) {
+        const bool in = t_lo + u < f.T;
+        xv[u] = in ? x[(size_t)(t_lo + u) * f.inner] : 0.0f;
+        gvv[u] = in ? ld_stream(g + (size_t)(t_lo + u) * f.inner) : 0.0f;
+      }
       {
         float m = m_in;
 #pragma unroll
         for (int u = 0; u < kBwdSeg; ++u) {
-          xv[u] = t_lo + u < f.T ? x[(size_t)(t_lo + u) * f.inner] : 0.0f;
           m = __fadd_rn(__fmul_rn(f.w, xv[u]), __fmul_rn(f.one_minus_w, m));
           mv[u] = m;
         }
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(kBwdThreads) pcen_bwd_kernel(const PcenBwdArgs
       for (int u = kBwdSeg - 1; u >= 0; --u) {
         const int t = t_lo + u;
         if (t < f.T) {
-          const float gv = ld_stream(g + (size_t)t * f.inner);
+          const float gv = gvv[u];
           const float xt = xv[u], m = mv[u];
           const float p = pcen_point(xt, m, f);           // the forward's value, bit for bit
           float dp = gv * two_over_r;
@@ -185,13 +207,13 @@ __global__ void __launch_bounds__(kBwdThreads) pcen_bwd_kernel(const PcenBwdArgs
           const float sm = exp2f(-f.gain * lg);            // s_t
           const float y = fmaf(xt, sm, f.bias);
           const float pw = p + f.bias_pow;                 // y^(1/r)
-          const float dpdy = f.inv_root * pw / y;
+          const float dpdy = __fdividef(f.inv_root * pw, y);
           const float dy = dp * dpdy;
-          d_bias += dy - dp * f.inv_root * f.bias_pow / f.bias;
+          d_bias += dy - dp * dpdb;
           d_root += dp * (ln_b * f.bias_pow - ln2 * __log2f(y) * pw) * f.inv_root * f.inv_root;
           const float ds = dy * xt;
           d_gain -= ds * ln2 * lg * sm;
-          const float dm = -f.gain * ds * sm / base_m;
+          const float dm = __fdividef(-f.gain * ds * sm, base_m);
           lam = fmaf(f.one_minus_w, lam, dm);              // l_t
           const float m_prev = u > 0 ? mv[u - 1] : m_in;
           d_smooth = fmaf(lam, xt - m_prev, d_smooth);

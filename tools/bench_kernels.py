@@ -41,6 +41,11 @@ for scope in ("tensor", "clip", "none"):
     passes = 1 if scope == "none" else 1.5          # reduce pass reads, apply pass reads and writes
     report(f"pcen [B,T,M] scope={scope}", timed(lambda: plan.pcen(mel, p)), B * T * M * 4 * 2 * passes, B)
 report("ema [B,T,M]", timed(lambda: plan.ema(mel, 0.04)), B * T * M * 4 * 2, B)
+gout = torch.randn_like(mel)
+for scope in ("tensor", "none"):   # algorithmic: read x, read dL/dout, write dL/dx
+    p = rt.pcen_params(norm_scope=scope)
+    report(f"pcen_backward [B,T,M] scope={scope}", timed(lambda: plan.pcen_backward(mel, gout, p)), B * T * M * 4 * 3, B)
+del gout
 for mode, reads in (("mag_pow", 1), ("power_to_db", 2), ("minmax", 2), ("std", 2)):
     report(f"compress {mode} (tensor-wide statistic)", timed(lambda: plan.compress(mel, mode, 0.27)), B * T * M * 4 * (reads + 1), B)
 report("frontend + pcen (bench.py step)", timed(lambda: plan.frontend_pcen(x)), B * (N * 4 + T * M * 4), B)
