@@ -268,7 +268,7 @@ def run_ours(args):
         # in flight the D2H of one batch overlaps the H2D of the next (PCIe is full duplex), which is how a data loader
         # would call it.  Every step's copies are inside the timed region.
         chunk = min(args.chunk, B)
-        n_pipes = 2
+        n_pipes = args.pipes
         pipes = [rt.HostPipe(plan, max_B=B, chunk=chunk) for _ in range(n_pipes)]
         h_in = [torch.empty((B, CLIP), dtype=torch.float32, pin_memory=True) for _ in range(n_pipes)]
         h_out = [torch.empty((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, pin_memory=True) for _ in range(n_pipes)]
@@ -299,7 +299,7 @@ def run_ours(args):
         e2e = {"value": world * B / dt, "unit": "clips/s", "h2d_bytes_per_step": B * CLIP * 4,
                "d2h_bytes_per_step": B * plan.n_frames * cfg.n_mels * 4, "steps": n_e2e * n_pipes,
                "api": "HostPipe.run (cacfe_hostpipe_run): pinned host -> H2D -> normalise/STFT/mel/PCEN -> D2H; "
-                      "2 pipes on 2 host threads, each step copies its own batch in and out",
+                      f"{n_pipes} pipes on {n_pipes} host threads, each step copies its own batch in and out",
                "checksum": float(h_out[0][0, :4, :4].sum())}
         del pipes, h_in, h_out
 
@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--pipes", type=int, default=2, help="host pipes (host threads) of the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rows", action="store_true", help="skip the standalone timing of the other HBM-bound rows")
