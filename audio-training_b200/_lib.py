@@ -74,6 +74,7 @@ PROTOTYPES = {
     "cacfe_signal_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cacfe_signal_components": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "cacfe_mix_up": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "cacfe_mel_from_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cacfe_ema": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),
     "cacfe_pcen": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int, c_longlong, c_int, c_int,

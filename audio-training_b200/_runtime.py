@@ -279,6 +279,19 @@ class Plan:
             return stats, {"mask": mask, "raw_mask": raw, "row_medians": rm, "column_medians": cm}
         return stats
 
+    def mix_up(self, one, two, lam):
+        """one * lam[b] + two * (1 - lam[b]) per batch entry (tfdataset.py:948)."""
+        one = self._check_in(one, "mix_up")
+        two = self._check_in(two, "mix_up")
+        lam = self._check_in(lam, "mix_up")
+        if one.shape != two.shape or lam.numel() != one.shape[0]:
+            raise ValueError("mix_up: shapes of the two batches / of lambda do not match")
+        out = torch.empty_like(one)
+        B = one.shape[0]
+        _lib.check(self._lib.cacfe_mix_up(self._handle, _ptr(one), _ptr(two), _ptr(lam), _ptr(out), B, one.numel() // B,
+                                          _stream(self.device)))
+        return out
+
     def compress(self, x, mode, param=0.0, per_clip=False):
         x = self._check_in(x, "compress")
         entries = x.shape[0] if per_clip else 1

@@ -1142,6 +1142,17 @@ int cacfe_signal_components(cacfe_plan* p, const float* spec, int K, int T, int 
   return check_launch(p, "signal_components", launches);
 }
 
+int cacfe_mix_up(cacfe_plan* p, const float* one, const float* two, const float* lambda, float* out, int B, long long per_entry,
+                 void* stream) {
+  if (!p || !one || !two || !lambda || !out) return fail(CACFE_EINVAL, "mix_up: null argument");
+  if (B < 1 || B > 65535 || per_entry < 1) return fail(CACFE_ESHAPE, "mix_up: bad shape");
+  CUDA_TRY(cudaSetDevice(p->device));
+  long long gx = (per_entry + 256 * 16 - 1) / (256 * 16);
+  if (gx > 1024) gx = 1024;
+  cacfe::mix_up_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(one, two, lambda, out, per_entry);
+  return check_launch(p, "mix_up");
+}
+
 int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float* out, long long entries,
                    long long per_entry, void* ws, void* stream) {
   if (!p || !in || !out) return fail(CACFE_EINVAL, "compress: null argument");

@@ -144,4 +144,26 @@ __global__ void __launch_bounds__(256) compress_kernel(const float* __restrict__
   }
 }
 
+// tfdataset.mix_up (tfdataset.py:948): images_one * l + images_two * (1 - l) with one l per batch entry, the reference's f32
+// operation order (three roundings).  grid = (blocks, B), block = 256.
+__global__ void __launch_bounds__(256) mix_up_kernel(const float* __restrict__ one, const float* __restrict__ two,
+                                                     const float* __restrict__ lam, float* __restrict__ out, long long per_entry) {
+  const float l = lam[blockIdx.y], r = __fsub_rn(1.0f, l);
+  const float* a = one + (size_t)blockIdx.y * per_entry;
+  const float* b = two + (size_t)blockIdx.y * per_entry;
+  float* y = out + (size_t)blockIdx.y * per_entry;
+  auto mix = [&](float u, float v) { return __fadd_rn(__fmul_rn(u, l), __fmul_rn(v, r)); };
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if ((per_entry & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+#pragma unroll 4
+    for (long long i = first; i < (per_entry >> 2); i += stride) {
+      const float4 u = ld_stream4(reinterpret_cast<const float4*>(a) + i), v = ld_stream4(reinterpret_cast<const float4*>(b) + i);
+      reinterpret_cast<float4*>(y)[i] = make_float4(mix(u.x, v.x), mix(u.y, v.y), mix(u.z, v.z), mix(u.w, v.w));
+    }
+  } else {
+    for (long long i = first; i < per_entry; i += stride) y[i] = mix(a[i], b[i]);
+  }
+}
+
 }  // namespace cacfe

@@ -197,3 +197,34 @@ def power_to_db(mel):
     """tfdataset.py:1906-1913 (== librosa.power_to_db(ref=np.max, top_db=80))."""
     t, restore = rt.to_device(mel)
     return restore(_any_plan(t.device.index).compress(t, "power_to_db"))
+
+
+def sample_beta_distribution(size, concentration_0=0.2, concentration_1=0.2, rng=None):
+    """tfdataset.py:921-924: Beta(c1, c0) as a ratio of two Gamma draws (host side; pass `rng` to make it repeatable)."""
+    rng = np.random.default_rng() if rng is None else rng
+    g1 = rng.gamma(concentration_1, size=size).astype(np.float32)
+    g2 = rng.gamma(concentration_0, size=size).astype(np.float32)
+    return g1 / (g1 + g2)
+
+
+def mix_up(ds_one, ds_two, global_epoch=None, alpha=0.2, chance=0.25, single_label=True, rng=None, lam=None):
+    """tfdataset.mix_up (tfdataset.py:929-955): per batch entry l ~ Beta(alpha, alpha), kept with probability `chance` (else 0);
+    images = one * l + two * (1 - l) on the device; labels mixed with l (or with l > 0.5 for single labels).  `global_epoch` is
+    accepted and -- as in the reference, whose decay line is commented out -- unused.  `lam` overrides the random draw."""
+    images_one, labels_one = ds_one
+    images_two, labels_two = ds_two
+    a, restore = rt.to_device(images_one)
+    b, _ = rt.to_device(images_two)
+    n = a.shape[0]
+    if lam is None:
+        rng = np.random.default_rng() if rng is None else rng
+        lam = sample_beta_distribution(n, alpha, alpha, rng)
+        lam = lam * (rng.random(n) < chance).astype(np.float32)
+    lam = np.asarray(lam, dtype=np.float32).reshape(n)
+    images = _any_plan(a.device.index).mix_up(a.contiguous(), b.contiguous(), torch.from_numpy(lam).to(a.device))
+    y_l = lam.reshape(n, 1)
+    if single_label:
+        y_l = (y_l > 0.5).astype(np.float32)
+    l1, l2 = np.asarray(labels_one, dtype=np.float32), np.asarray(labels_two, dtype=np.float32)
+    labels = l1 * y_l + l2 * (1 - y_l)
+    return restore(images), labels

@@ -183,6 +183,11 @@ int cacfe_signal_components(cacfe_plan* plan, const float* spec_dev, int K, int 
                             float* col_medians_dev, int32_t* comps_dev, int max_components, int32_t* n_components_dev,
                             void* workspace_dev, void* stream);
 
+/* ---- tfdataset.mix_up tfdataset.py:929-955: out[b] = one[b] * lambda[b] + two[b] * (1 - lambda[b]) over per_entry floats per
+ * batch entry (f32, the reference's operation order); lambda_dev: device float[B].  The Beta / Bernoulli draws stay on the host. */
+int cacfe_mix_up(cacfe_plan* plan, const float* one_dev, const float* two_dev, const float* lambda_dev, float* out_dev, int B,
+                 long long per_entry, void* stream);
+
 /* ---- a12-a14: point-wise compression with a tensor- (entries = 1) or clip-wide (entries = B) statistic. */
 int cacfe_compress(cacfe_plan* plan, int mode, float param, const float* in_dev, float* out_dev, long long entries,
                    long long per_entry, void* workspace_dev, void* stream);

@@ -608,3 +608,23 @@ def test_signal_noise_end_to_end(oracle):
         assert np.all(np.abs(got[:, 2:4] - want[:, 2:4]) <= 48000 / 2048 + 1e-9)
         assert np.all(np.abs(got[:, 4] - want[:, 4]) <= 0.01 * want[:, 4] + 2)
     assert it.get_end(oracle.synth_recording(4.0, seed=2), 48000) == 4.0
+
+
+def test_mix_up(oracle):
+    """tfdataset.mix_up (tfdataset.py:929-955): the device blend is the reference's f32 expression, bit for bit."""
+    rng = np.random.default_rng(4)
+    one, two = rng.standard_normal((6, 1001)).astype(np.float32), rng.standard_normal((6, 1001)).astype(np.float32)
+    y1, y2 = np.eye(6, 4, dtype=np.float32), np.eye(6, 4, 1, dtype=np.float32)
+    lam = np.array([0.0, 0.3, 0.5, 0.7, 1.0, 0.123456], np.float32)
+    img, lab = td.mix_up((one, y1), (two, y2), lam=lam)
+    x_l = lam.reshape(6, 1)
+    assert np.array_equal(img, one * x_l + two * (1 - x_l))
+    y_l = (x_l > 0.5).astype(np.float32)
+    assert np.array_equal(lab, y1 * y_l + y2 * (1 - y_l))
+    big = torch.rand(3, 160, 513, 3, device="cuda")
+    out, _ = td.mix_up((big, y1[:3]), (big.flip(0), y2[:3]), lam=lam[1:4], single_label=False)
+    ref = big * torch.from_numpy(lam[1:4]).cuda().view(3, 1, 1, 1) + big.flip(0) * (1 - torch.from_numpy(lam[1:4]).cuda().view(3, 1, 1, 1))
+    assert out.is_cuda and torch.equal(out, ref)
+    img2, _ = td.mix_up((one, y1), (two, y2), rng=np.random.default_rng(9), chance=1.0)
+    img3, _ = td.mix_up((one, y1), (two, y2), rng=np.random.default_rng(9), chance=1.0)
+    assert np.array_equal(img2, img3) and not np.array_equal(img2, one)
