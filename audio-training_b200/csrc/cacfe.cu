@@ -443,12 +443,13 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok) {
-    const void* kernels[5] = {(const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC>,
-                              (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM>,
-                              (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC>,
-                              (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM>,
-                              (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC>};
-    for (int q = 0; q < 5 && e == cudaSuccess; ++q)
+    const void* kernels[10] = {
+#define CACFE_V3_K(NQ_, LAYOUT_) (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false>, (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true>
+        CACFE_V3_K(33, cacfe::LAYOUT_SPEC), CACFE_V3_K(15, cacfe::LAYOUT_BTM), CACFE_V3_K(15, cacfe::LAYOUT_BMTC),
+        CACFE_V3_K(33, cacfe::LAYOUT_BTM), CACFE_V3_K(33, cacfe::LAYOUT_BMTC)
+#undef CACFE_V3_K
+    };
+    for (int q = 0; q < 10 && e == cudaSuccess; ++q)
       // the attribute belongs to the function, not to the plan: always the device maximum, so that a plan created later
       // with a smaller layout cannot shrink it under an earlier plan
       e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -714,16 +715,24 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     const bool btm = layout == CACFE_LAYOUT_BTM || via_staging;
     mj.spec_ratio = cacfe::kFft / p->cfg.n_fft;
     mj.spec_bins = p->n_bins;
+    // n_fft = 4096: Hann window computed per thread (WINC); shorter transforms read the zero-padded window table
+    const bool winc = p->cfg.n_fft == cacfe::kFft;
+#define CACFE_V3_LAUNCH(NQ_, LAYOUT_)                                                                                             \
+  do {                                                                                                                            \
+    if (winc) cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);    \
+    else cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);        \
+  } while (0)
     if (layout == cacfe::LAYOUT_SPEC)
-      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPEC);
     else if (p->nq_v3 <= 15 && btm)
-      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      CACFE_V3_LAUNCH(15, cacfe::LAYOUT_BTM);
     else if (p->nq_v3 <= 15)
-      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      CACFE_V3_LAUNCH(15, cacfe::LAYOUT_BMTC);
     else if (btm)
-      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BTM><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      CACFE_V3_LAUNCH(33, cacfe::LAYOUT_BTM);
     else
-      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_BMTC><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      CACFE_V3_LAUNCH(33, cacfe::LAYOUT_BMTC);
+#undef CACFE_V3_LAUNCH
   } else {
     if (layout == cacfe::LAYOUT_SPEC)
       return fail(CACFE_EINVAL, "stft: the spectrogram output needs the persistent kernel (16-byte aligned input, n_samples %% 4 == 0)");

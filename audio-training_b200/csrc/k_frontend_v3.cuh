@@ -28,6 +28,7 @@
 #include "cacfe_async.cuh"  // mbarrier / bulk-copy wrappers
 #include "fft64x2_gen.cuh"
 #include "mel_jobs.h"
+#include "win_consts.cuh"
 
 namespace cacfe {
 
@@ -70,7 +71,10 @@ struct MelArgs {
   int spec_ratio, spec_bins;   // LAYOUT_SPEC: 4096 / n_fft and n_fft / 2 + 1
 };
 
-template <int NQ, int LAYOUT>
+// WINC: the Hann(4096) window is computed per thread by angle addition (two FFMA with immediates per value) instead of being
+// read from shared memory (one LDS.64 per two values): the kernel is shared-memory-wavefront bound, not FMA bound.  Shorter
+// transforms (zero-padded window) keep the table.
+template <int NQ, int LAYOUT, bool WINC = false>
 __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const FrontendArgs a, const MelArgs mj,
                                                                       const int total_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -219,7 +223,6 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   const int j = stage2_row(t64);
   const bool self = (j == 0) || (j == 32);
   const int plane = self ? lane : (lane ^ 16);
-
   // The six groups run free: there is no CTA-wide barrier in the loop, only the two mbarrier hand-overs per tile.
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i & 1;
@@ -250,10 +253,22 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
         // ---- stage 1 input: window; z[n] = w[n] (xA[n] + i xB[n]), thread n2 = t64 holds n = 64 q + n2 ----------------
         const float* fa = tile + (2 * g) * a.hop;
         const float* fb = fa + a.hop;
+        float win_c = 0.0f, win_s = 0.0f;   // (cos, sin) of phi_t = 2 pi t / 4096: re-read per pair (two registers that must not
+        if (WINC) {                         // stay live across the DFT) from the twiddle row of k = 1: (cos, -sin)(2 pi n2 / 4096)
+          const float4 t1 = s_tw4[t64];
+          win_c = t1.y;
+          win_s = -t1.w;
+        }
 #pragma unroll
         for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
           const int n = 64 * q + t64;
-          const float2 w2 = s_win2[(q >> 1) * 64 + t64];
+          float2 w2;
+          if (WINC) {
+            w2.x = fmaf(kWinA[q], win_c, fmaf(kWinB[q], win_s, 0.5f));
+            w2.y = fmaf(kWinA[q + 1], win_c, fmaf(kWinB[q + 1], win_s, 0.5f));
+          } else {
+            w2 = s_win2[(q >> 1) * 64 + t64];
+          }
           const cacfe_f2 wv = cacfe_pk(w2.x, w2.y);
           const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv);
           const cacfe_f2 xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
@@ -267,6 +282,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       cacfe_fft64x2(re, im);
       if (ph == 0) {
         // ---- twiddle W4096^(n2 k1), then the transpose through shared memory, real parts first ------------------------
+        // (measured alternative: a two-level table, W^(n2 k1) = W^(n2 8 a) W^(n2 b) with the four b-pairs in registers -- 11
+        // LDS.128 instead of 32 per thread and pass, one more packed complex product per output pair, four FFT groups for the
+        // registers: 10.15 ms against 9.88 ms per 4096 clips.  The extra FMA work costs what the saved wavefronts gain.)
 #pragma unroll
         for (int k = 0; k < 64; k += 2) {  // outputs k, k + 1 leave cacfe_fft64x2 in one register pair
           const int s0 = k, s1 = k + 1;
