@@ -3,8 +3,10 @@
 // custommel.mel_f (custommel.py:18-54) gives a [n_mels][n_bins] bank whose rows are short runs of non-zeros (3..30
 // taps for the reference's 160-band bank).  A 64-thread FFT group owns the power of one frame pair; its threads
 // share the bands out so that every thread sees about the same number of taps:
-//   segment s < n_mels / 64 : band 64 s + t (s even) or 64 s + 63 - t (s odd)      -- widths grow with the band index
-//   last, short segment     : (n_mels % 64 <= 32) each band is cut in two halves for lanes 2i / 2i+1, summed by shuffle
+//   segment s < n_mels / 64 : bands 64 s .. 64 s + 63, one per thread
+//   last, short segment     : (n_mels % 64 <= 32) each band is cut in two halves for a lane pair 2i / 2i+1, summed by shuffle
+// Which lane of its warp a band sits on, and at which 16-byte chunk its reads start, is chosen to keep the power loads free of
+// shared-memory bank conflicts (see below).
 // The weights are stored times 1/4 (exact): the kernel keeps 4 |X|^2 (or 4 |X|), see k_frontend_v3.cuh.
 // Taps are consumed four bins at a time ("quads": one 16-byte weight load, two 16-byte power loads, 8 FMAs).  Every
 // thread of a segment runs the same number of quads; the surplus taps carry weight 0.
@@ -87,16 +89,102 @@ inline MelJobs build_mel_jobs(const float* bank, int n_mels, int n_bins, int n_c
     J.nq[s] = q;
     J.total_quads += q;
   }
+  // ---- shared-memory bank conflicts of the power loads ---------------------------------------------------------------
+  // A thread reads 16-byte chunks c0, c0 + 1, ... of the power buffer; the eight lanes of a quarter-warp are served
+  // together and collide unless their chunk indices differ mod 8 (ncu: 55 % of those wavefronts were replays with every
+  // band starting at its own first bin).  Two freedoms, both free of arithmetic: a band may start up to `slack` chunks
+  // early (the extra taps carry weight 0, the quad count of the segment is what its widest band needs anyway), and the
+  // bands of a segment may sit on any lane of their warp (the kernel takes band and chunk from the descriptor; the halves of
+  // a split band stay on a lane pair).  Greedy: units with the fewest feasible residues first, each into the first
+  // quarter-warp that still has distinct residues for it.
+  std::vector<int> c0_of(kMelMaxSeg * 64, 0);
+  for (int s = 0; s < J.nseg; ++s) {
+    const int span = n_chunks - 2 * J.nq[s];
+    auto range_of = [&](const Job& j, int& lo, int& hi) {
+      lo = 0;
+      hi = span;
+      if (j.valid && j.kb >= j.ka) {
+        hi = std::min(j.ka >> 1, span);
+        lo = std::max(0, (j.kb + 1 - 4 * J.nq[s] + 1) >> 1);
+        if (lo > hi) lo = hi;
+      }
+    };
+    const int unit = (J.split_seg == s) ? 2 : 1;
+    for (int w = 0; w < 2; ++w) {
+      const int base = s * 64 + 32 * w;
+      std::vector<int> order(32 / unit);
+      for (int u = 0; u < 32 / unit; ++u) order[u] = u;
+      auto n_feasible = [&](int u) {
+        int n = 0;
+        for (int e = 0; e < unit; ++e) {
+          int lo, hi;
+          range_of(jobs[base + u * unit + e], lo, hi);
+          n += std::min(8, hi - lo + 1);
+        }
+        return n;
+      };
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_feasible(a) < n_feasible(b); });
+      int members[4] = {0, 0, 0, 0};
+      bool used[4][8] = {};
+      Job placed[32];
+      int placed_c0[32];
+      int slot_of_group[4][8];
+      for (int u : order) {
+        int pick[2] = {0, 0}, group = -1;
+        for (int g = 0; g < 4 && group < 0; ++g) {
+          if (members[g] + unit > 8) continue;
+          bool taken[8];
+          for (int r = 0; r < 8; ++r) taken[r] = used[g][r];
+          bool ok = true;
+          for (int e = 0; e < unit && ok; ++e) {
+            int lo, hi;
+            range_of(jobs[base + u * unit + e], lo, hi);
+            int found = -1;
+            for (int c = hi; c >= lo && c > hi - 8; --c)
+              if (!taken[c & 7]) {
+                found = c;
+                break;
+              }
+            if (found < 0) ok = false;
+            else {
+              taken[found & 7] = true;
+              pick[e] = found;
+            }
+          }
+          if (ok) group = g;
+        }
+        if (group < 0) {  // no conflict-free place left: the emptiest quarter-warp, at the band's own first chunk
+          for (int g = 0; g < 4; ++g)
+            if (members[g] + unit <= 8 && (group < 0 || members[g] < members[group])) group = g;
+          for (int e = 0; e < unit; ++e) {
+            int lo, hi;
+            range_of(jobs[base + u * unit + e], lo, hi);
+            pick[e] = hi;
+          }
+        }
+        for (int e = 0; e < unit; ++e) {
+          used[group][pick[e] & 7] = true;
+          slot_of_group[group][members[group]] = u * unit + e;
+          const int lane = 8 * group + members[group]++;
+          placed[lane] = jobs[base + u * unit + e];
+          placed_c0[lane] = pick[e];
+        }
+      }
+      (void)slot_of_group;
+      for (int l = 0; l < 32; ++l) {
+        jobs[base + l] = placed[l];
+        c0_of[base + l] = placed_c0[l];
+      }
+    }
+  }
   J.w.assign((size_t)std::max(J.total_quads, 1) * 64 * 4, 0.0f);
   J.desc.assign(kMelMaxSeg * 64, 0);
   int qbase = 0;
   for (int s = 0; s < J.nseg; ++s) {
     for (int t = 0; t < 64; ++t) {
       const Job& j = jobs[s * 64 + t];
-      int c0 = 0;
+      const int c0 = c0_of[s * 64 + t];
       if (j.valid && j.kb >= j.ka) {
-        c0 = j.ka >> 1;
-        if (c0 + 2 * J.nq[s] > n_chunks) c0 = n_chunks - 2 * J.nq[s];  // stay inside the buffer: pad in front instead
         for (int i = 0; i < J.nq[s]; ++i)
           for (int e = 0; e < 4; ++e) {
             const int bin = 2 * c0 + 4 * i + e;
