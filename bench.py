@@ -240,7 +240,7 @@ def run_ours(args):
     traffic = None
     try:
         import re
-        txt = open(os.path.join(REPO, "profiles", "r01_k1_v3_ncu_summary.txt")).read()
+        txt = open(os.path.join(REPO, "profiles", "r01_k1_v5_ncu_summary.txt")).read()
         rd = float(re.search(r"dram__bytes_read\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
         wr = float(re.search(r"dram__bytes_write\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
         traffic = (rd + wr) * 1e6 / 1024.0 * B
@@ -332,7 +332,7 @@ def run_ours(args):
         rows["pcen_tensor_scope"] = row(alone(lambda: plan.pcen(mel, params)), B, 2 * feat, 3 * feat)
         rows["pcen_no_minmax"] = row(alone(lambda: plan.pcen(mel, rt.pcen_params(norm_scope="none"))), B, 2 * feat, 2 * feat)
         rows["ema"] = row(alone(lambda: plan.ema(mel, 0.04)), B, 2 * feat, 2 * feat)
-        rows["normalize"] = row(alone(lambda: plan.normalize(x)), B, 2 * CLIP * 4, 3 * CLIP * 4)
+        rows["normalize"] = row(alone(lambda: plan.normalize(x)), B, 2 * CLIP * 4, 2 * CLIP * 4)   # cluster kernel: one read, one write
         rows["minmax_epilogue"] = row(alone(lambda: plan.compress(mel, "minmax")), B, 2 * feat, 3 * feat)
         del mel
         nb = min(B, 384)
