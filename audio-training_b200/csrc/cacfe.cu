@@ -750,8 +750,13 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     p->k1_events.emplace_back(ev0, ev1);
   }
   if (v3 && layout == CACFE_LAYOUT_BMTC && staging != nullptr) {
-    dim3 grid((p->cfg.n_mels + 31) / 32, (p->n_frames + 31) / 32, B);
-    cacfe::btm_to_bmtc_kernel<<<grid, dim3(32, 8), 0, st>>>(staging, feat, p->n_frames, p->cfg.n_mels, channels);
+    dim3 grid((p->cfg.n_mels + 31) / 32, (p->n_frames + cacfe::kImgT - 1) / cacfe::kImgT, B);
+    if (channels == 1)
+      cacfe::btm_to_bmtc_kernel<1><<<grid, dim3(32, 8), 0, st>>>(staging, feat, p->n_frames, p->cfg.n_mels, channels);
+    else if (channels == 3)
+      cacfe::btm_to_bmtc_kernel<3><<<grid, dim3(32, 8), 0, st>>>(staging, feat, p->n_frames, p->cfg.n_mels, channels);
+    else
+      cacfe::btm_to_bmtc_kernel<0><<<grid, dim3(32, 8), 0, st>>>(staging, feat, p->n_frames, p->cfg.n_mels, channels);
     ++launches;
   }
   return check_launch(p, "frontend", launches);

@@ -508,24 +508,28 @@ __global__ void __launch_bounds__(256) spec_transpose_kernel(const float* __rest
 }
 
 // [B][T][M] (what the FFT kernel stores coalesced) -> the reference image [B][M][T][C] with the channel repeat of
-// raw_to_mel (tfdataset.py:2052-2053).  32 x 32 tiles through shared memory; each output row piece is 32 * C
-// contiguous floats.  grid = (ceil(M/32), ceil(T/32), B), block = (32, 8).
+// raw_to_mel (tfdataset.py:2052-2053).  Tiles of 64 frames x 32 bands through shared memory: 128-byte reads, and each output
+// row piece is 64 * C contiguous floats (768 bytes for C = 3); 8 loads in flight per thread.
+// grid = (ceil(M/32), ceil(T/64), B), block = (32, 8).
+constexpr int kImgT = 64;
+template <int C>   // 0: runtime channel count
 __global__ void __launch_bounds__(256) btm_to_bmtc_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int M,
-                                                          int C) {
-  __shared__ float tile[32][33];
+                                                          int channels) {
+  __shared__ float tile[kImgT][33];
   const size_t b = blockIdx.z;
-  const int m0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int t = t0 + r, m = m0 + threadIdx.x;
-    tile[r][threadIdx.x] = (t < T && m < M) ? in[(b * T + t) * M + m] : 0.0f;
-  }
+  const int m0 = blockIdx.x * 32, t0 = blockIdx.y * kImgT;
+  const int nt = min(kImgT, T - t0);
+  const int m_in = m0 + threadIdx.x;
+#pragma unroll
+  for (int r = threadIdx.y; r < kImgT; r += 8)
+    if (r < nt && m_in < M) tile[r][threadIdx.x] = ld_stream(in + (b * T + t0 + r) * M + m_in);
   __syncthreads();
-  const int nt = min(32, T - t0);
+  const int cn = C > 0 ? C : channels;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int m = m0 + r;
     if (m >= M) continue;
-    float* o = out + ((b * M + m) * T + t0) * C;
-    for (int i = threadIdx.x; i < nt * C; i += 32) o[i] = tile[i / C][r];
+    float* o = out + ((b * M + m) * T + t0) * cn;
+    for (int i = threadIdx.x; i < nt * cn; i += 32) o[i] = tile[C > 0 ? i / C : i / cn][r];
   }
 }
 
