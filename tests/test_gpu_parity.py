@@ -280,6 +280,29 @@ def test_path_c_streaming_edges(oracle):
     assert torch.equal(a, b) and float(a[:, 3:5].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_path_c_streaming_random_banks(oracle, seed):
+    """Random mel-style banks (custommel.mel_f with random band counts, frequency ranges, break frequencies and transform
+    sizes -- narrow ranges give empty and single-bin bands) on random shapes: the streaming kernel, wherever the plan takes
+    it, is bit-identical to the per-column kernel and both match a float64 product."""
+    rng = np.random.default_rng(100 + seed)
+    n_fft = int(rng.choice([256, 512, 1024, 4096]))
+    K = n_fft // 2 + 1
+    n_mels = int(rng.integers(4, 200))
+    f0 = float(rng.uniform(0, 4000))
+    f1 = float(rng.uniform(f0 + 500, 24000))
+    fb = oracle.mel_f(48000, n_mels, f0, f1, n_fft, float(rng.choice([700, 1000, 1750]))).astype(np.float32)
+    if seed % 3 == 0:
+        fb[rng.integers(0, n_mels, 3)] = 0.0                                  # empty bands
+    B, T = int(rng.integers(1, 40)), int(rng.integers(1, 769))
+    power, channels = int(rng.choice([1, 2])), int(rng.choice([1, 2, 3]))
+    spec = torch.rand((B, K, T), device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)) * 2
+    a, b = _both_path_c(rt.FrontendConfig(n_fft=n_fft, hop=max(1, n_fft // 8), n_mels=n_mels, power=power, channels=channels), fb, spec)
+    assert a.shape == (B, n_mels, T, channels) and torch.equal(a, b)
+    want = np.einsum("mk,bkt->bmt", fb.astype(np.float64), spec.cpu().numpy().astype(np.float64) ** power)
+    check(oracle, a[..., channels - 1], want, what="random bank")
+
+
 @pytest.mark.parametrize("power,layout,channels", [(1, "bmtc", 1), (2, "bmtc", 3), (1, "btm", 1)])
 def test_path_c_tensor_core(oracle, xn, bank, power, layout, channels):
     """tcgen05 banded 3xTF32 GEMM (k_melspec_tc.cuh) against the f64 oracle and against the banded FP32 kernel."""
