@@ -135,6 +135,37 @@ def test_short_and_ragged_clips(oracle):
         check(oracle, out[..., 0], oracle.raw_to_mel(x, w, channels=0), what=f"n={n}")
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_fused_kernel_random_configurations(oracle, seed):
+    """The persistent fused kernel away from the reference's one configuration: random hop, clip length, band count,
+    frequency range, framing (TF pad_end / no pad / librosa centre with zeros or reflection), power, layout and fused
+    normalisation, against the float64 oracle."""
+    rng = np.random.default_rng(500 + seed)
+    hop = int(rng.integers(64, 465))
+    n = 4 * int(rng.integers(1500, 12000))                                      # 6 000 .. 48 000 samples, n % 4 == 0
+    n_mels = int(rng.choice([32, 64, 96, 120, 160, 192]))
+    fmin = float(rng.uniform(0, 1500))
+    fmax = float(rng.uniform(4000, 23000))
+    framing = str(rng.choice(["tf_pad_end", "no_pad", "center_zero", "center_reflect"]))
+    power = int(rng.choice([1, 2]))
+    norm = bool(rng.integers(0, 2))
+    layout, channels = [("btm", 1), ("bmtc", 1), ("bmtc", 3)][int(rng.integers(0, 3))]
+    x = (rng.standard_normal((3, n)) * 0.2 + rng.uniform(-0.5, 0.5, (3, 1))).astype(np.float32)
+    bank = oracle.mel_f(48000, n_mels, fmin, fmax, 4096, 1000)
+    cfg = rt.FrontendConfig(n_samples=n, hop=hop, framing=framing, n_mels=n_mels, fmin=fmin, fmax=fmax, power=power,
+                            channels=channels, out_layout=layout, normalize=norm)
+    got = rt.Plan(cfg, 0).frontend(torch.from_numpy(x).cuda()).cpu().numpy()
+    xin = oracle.normalize(x, np.float32) if norm else x
+    if framing in ("tf_pad_end", "no_pad"):
+        want = oracle.raw_to_mel(xin, bank, 4096, hop, framing == "tf_pad_end", 0, power)             # [B, M, T]
+    else:
+        mode = "constant" if framing == "center_zero" else "reflect"
+        want = np.stack([oracle.get_spect(c, hop_length=hop, n_mels=n_mels, fmin=fmin, fmax=fmax, power=power, pad_mode=mode)[..., 0]
+                         for c in xin])
+    got = np.swapaxes(got, 1, 2) if layout == "btm" else got[..., channels - 1]
+    check(oracle, got, want, what=f"hop {hop} n {n} mels {n_mels} {framing} power {power} norm {norm} {layout}")
+
+
 def test_batch_invariance(oracle):
     """Sharding invariance: a clip's features do not depend on its batch mates or its position in the batch."""
     x = torch.from_numpy(oracle.synth_clips(np.arange(8, 8 + 37))).cuda()
@@ -407,6 +438,36 @@ def test_pcen(oracle, golden):
     check(oracle, per_clip, want, what="clip scope")
     raw = atb.PCEN(norm_scope="none")(x)
     check(oracle, raw, oracle.pcen_raw(x), what="no min-max")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_pcen_random_parameters(oracle, seed):
+    """PCEN with random layer weights (also outside their clip ranges), shapes, layouts and min-max scopes against the
+    float64 oracle; the lane kernel and the warp-scan kernel are both reached (inner size 1..3 with T >= 32 takes the scan)."""
+    rng = np.random.default_rng(900 + seed)
+    kw = dict(gain=float(rng.uniform(0.3, 1.2)), bias=float(rng.uniform(0.5, 4.0)), root=float(rng.uniform(0.8, 4.0)),
+              smooth=float(rng.uniform(-0.05, 0.6)))
+    scope = str(rng.choice(["tensor", "clip", "none"]))
+    if seed % 2:
+        shape, axis = (int(rng.integers(1, 6)), int(rng.integers(1, 200)), int(rng.integers(1, 70))), 1      # [B, T, F]
+    else:
+        shape, axis = (int(rng.integers(1, 4)), 8 * int(rng.integers(1, 5)), int(rng.integers(32, 300)), int(rng.integers(1, 4))), 2
+    x = (rng.random(shape) ** 4 * 20 + 1e-4).astype(np.float32)
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    got = plan.pcen(torch.from_numpy(x).cuda(), rt.pcen_params(norm_scope=scope, **kw), axis).cpu().numpy()
+    raw = oracle.pcen_raw(x, axis=axis, **kw)
+    if scope == "tensor":
+        want = 2 * (raw - raw.min()) / (raw.max() - raw.min()) - 1
+    elif scope == "clip":
+        ax = tuple(range(1, raw.ndim))
+        mn, mx = raw.min(axis=ax, keepdims=True), raw.max(axis=ax, keepdims=True)
+        want = 2 * (raw - mn) / (mx - mn) - 1
+    else:
+        want = raw
+    if np.isfinite(want).all():
+        check(oracle, got, want, 2.0, what=f"pcen {kw} {scope} {shape}")
+    else:                                                                # a constant tensor / clip: 0 / 0 in the reference too
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
 
 
 def test_pcen_image_extension(oracle, golden):
