@@ -965,9 +965,9 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
   a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
   cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<grid, g.block, 0, st>>>(a);
   if (a.per_clip_extremes)
-    cacfe::minmax_finalize_kernel<<<B, 256, 0, st>>>(partial, g.gx, extremes);
+    cacfe::pcen_extremes_kernel<<<B, 256, 0, st>>>(partial, g.gx, extremes, a, 0);
   else
-    cacfe::minmax_finalize_kernel<<<1, 256, 0, st>>>(partial, B * g.gx, extremes);
+    cacfe::pcen_extremes_kernel<<<1, 256, 0, st>>>(partial, B * g.gx, extremes, a, 0);
   cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<grid, g.block, 0, st>>>(a);
   return check_launch(p, "pcen", 3);
 }
@@ -1050,7 +1050,7 @@ int cacfe_pcen_backward(cacfe_plan* p, const cacfe_pcen_params* q, const float* 
     const int per_entry = q->norm_scope == CACFE_NORM_CLIP ? g.gx : B * g.gx;
     a.f.partial = (float2*)(w + off[0]);
     cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, B), g.block, 0, st>>>(a.f);
-    cacfe::minmax_fold_raw_kernel<<<entries, 256, 0, st>>>(a.f.partial, per_entry, extremes);
+    cacfe::pcen_extremes_kernel<<<entries, 256, 0, st>>>(a.f.partial, per_entry, extremes, a.f, 1);   // (mn, mx) of p
     cacfe::pcen_bwd_reduce_kernel<<<dim3(g.gx, B), g.block, 0, st>>>(a);
     cacfe::pcen_bwd_fold_kernel<<<entries, 32, 0, st>>>(partial, per_entry, extremes, fold);
     launches += 4;
@@ -1385,7 +1385,7 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
     } else {
       cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
       if (!global) {
-        cacfe::minmax_finalize_kernel<<<nb, 256, 0, st>>>(ac.partial, g.gx, h->d_extremes + b0);
+        cacfe::pcen_extremes_kernel<<<nb, 256, 0, st>>>(ac.partial, g.gx, h->d_extremes + b0, ac, 0);
         cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
       }
     }
@@ -1402,7 +1402,7 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
     upload_gate.unlock();
     // phase 2: tensor-global extremes need every chunk (tfpcen.py:105-110)
     CUDA_TRY(cudaStreamWaitEvent(h->stream[0], h->done[1], 0));
-    cacfe::minmax_finalize_kernel<<<1, 256, 0, h->stream[0]>>>(h->d_partial, B * g.gx, h->d_extremes);
+    cacfe::pcen_extremes_kernel<<<1, 256, 0, h->stream[0]>>>(h->d_partial, B * g.gx, h->d_extremes, a, 0);
     if ((rc = check_launch(p, "hostpipe")) != CACFE_OK) return rc;
     CUDA_TRY(cudaEventRecord(h->all_reduced, h->stream[0]));
     CUDA_TRY(cudaStreamWaitEvent(h->stream[1], h->all_reduced, 0));

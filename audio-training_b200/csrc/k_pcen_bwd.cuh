@@ -11,6 +11,7 @@
 // adjoint is the reverse-time recurrence  l_t = dM_t + (1 - w) l_{t+1}.
 //
 // Three launches (two when norm_scope = NONE), same thread <-> lane map as pcen_kernel:
+//   (extremes: pcen_kernel<REDUCE> + pcen_extremes_kernel in raw (mn, mx) form -- the range alone does not give mx back exactly)
 //   pcen_bwd_reduce_kernel   recomputes p (same instruction sequence as the forward: extremes compare bit for bit) and
 //                            accumulates per block  sum G, sum G p, #(p == mn), #(p == mx)          reads x, G
 //   pcen_bwd_fold_kernel     folds the partials into  2/R, dL/dmx / n_max, dL/dmn / n_min           tiny
@@ -51,20 +52,6 @@ __device__ __forceinline__ double block_sum_d(double v, double* scratch) {
   if (threadIdx.x == 0)
     for (int i = 0; i < nwarp; ++i) s += scratch[i];
   return s;   // valid in thread 0
-}
-
-// (mn, mx) themselves -- minmax_finalize_kernel stores (range, mn), from which mx cannot be recovered exactly
-__global__ void __launch_bounds__(256) minmax_fold_raw_kernel(const float2* __restrict__ partial, int per_entry,
-                                                              float2* __restrict__ extremes) {
-  __shared__ float scratch[64];
-  const float2* p = partial + (size_t)blockIdx.x * per_entry;
-  float mn = INFINITY, mx = -INFINITY;
-  for (int i = threadIdx.x; i < per_entry; i += blockDim.x) {
-    mn = fminf(mn, p[i].x);
-    mx = fmaxf(mx, p[i].y);
-  }
-  block_minmax(mn, mx, scratch);
-  if (threadIdx.x == 0) extremes[blockIdx.x] = make_float2(mn, mx);
 }
 
 __global__ void __launch_bounds__(256) pcen_bwd_reduce_kernel(const PcenBwdArgs a) {
