@@ -25,18 +25,21 @@ def mel_freq(f):
 
 
 class Signal:
-    """The five fields identifytracks.Signal is built from (:376-394) plus the derived mel range."""
+    """Plain record with the constructor identifytracks.Signal has (:376-394): (start, end, freq_start, freq_end, mass), plus
+    the derived mel range.  Pass `signal_class=` to signal_noise to get the reference's own class instead."""
+    __slots__ = ("start", "end", "freq_start", "freq_end", "mass", "mel_freq_start", "mel_freq_end", "predictions", "track_id")
 
     def __init__(self, start, end, freq_start, freq_end, mass):
-        self.start, self.end, self.freq_start, self.freq_end, self.mass = start, end, freq_start, freq_end, mass
+        for name, value in zip(self.__slots__[:5], (start, end, freq_start, freq_end, mass)):
+            setattr(self, name, value)
         self.mel_freq_start, self.mel_freq_end = mel_freq(freq_start), mel_freq(freq_end)
         self.predictions, self.track_id = [], None
 
     def to_array(self):
-        return [self.start, self.end, self.freq_start, self.freq_end]
+        return [getattr(self, k) for k in self.__slots__[:4]]
 
     def __repr__(self):
-        return f"Signal: {self.start}-{self.end} f: {self.freq_start}-{self.freq_end} mass {self.mass}"
+        return "Signal(%.3f-%.3f s, %.1f-%.1f Hz, mass %d)" % (self.start, self.end, self.freq_start, self.freq_end, self.mass)
 
 
 def get_nfft(sr):
@@ -44,18 +47,18 @@ def get_nfft(sr):
 
 
 def _bins(sr, n_fft):
-    """The loop over librosa.fft_frequencies of identifytracks.py:60-73 -> (freqs, lower_bin, upper_bin, height)."""
+    """What the loop over librosa.fft_frequencies computes (identifytracks.py:60-73), in closed form: with i0 the first
+    bin above 100 Hz, lower_bin = i0 - 1 and height = i0 + 1; upper_bin = the first bin above 20 kHz (0 when there is none).
+    -> (freqs, lower_bin, upper_bin, height)."""
     freqs = np.fft.rfftfreq(n_fft, 1.0 / sr)
-    lower_bin, upper_bin, height = None, 0, 0
-    for i, f in enumerate(freqs):
-        if f > 100 and lower_bin is None:
-            lower_bin = i - 1
-        if f > 20000:
-            upper_bin = i
-            break
-        if f > 100 and height == 0:
-            height = i + 1
-    return freqs, lower_bin, upper_bin, height
+    above = np.flatnonzero(freqs > 100)
+    top = np.flatnonzero(freqs > 20000)
+    stop = int(top[0]) if len(top) else len(freqs)          # the reference's loop breaks there
+    if len(above) == 0 or above[0] > stop:
+        return freqs, None, int(top[0]) if len(top) else 0, 0
+    i0 = int(above[0])
+    height = i0 + 1 if i0 < stop else 0
+    return freqs, i0 - 1, int(top[0]) if len(top) else 0, height
 
 
 _plans = {}   # (padded length, n_fft, hop, device) -> Plan; a handful of recording lengths, oldest dropped first
@@ -98,16 +101,15 @@ def signal_noise(frames, sr, hop_length=281, n_fft=1024, min_width=None, min_hei
     plan = rt.get_plan(rt.FrontendConfig(), device)
     out = plan.signal_components(spec, 4, (height, width), ero, debug=return_debug)
     stats, debug = out if return_debug else (out, None)
-    stats = sorted(stats.tolist(), key=lambda s: s[0])  # stable, like the reference's sort by x (:110-111)
-    if min_height is None:
-        min_height = height - height // 10
-    if min_width is None:
-        min_width = 0.65 * width
-    stats = [s for s in stats if s[2] > min_width and s[3] > min_height]
-    signals = []
-    for s in stats:
-        max_freq = min(len(freqs) - 1, s[1] + s[3])
-        signals.append(signal_class(s[0] * 281 / sr, (s[0] + s[2]) * 281 / sr, freqs[s[1]], freqs[max_freq], s[4]))
+    rows = np.asarray(stats, dtype=np.int64).reshape(-1, 5)
+    rows = rows[np.argsort(rows[:, 0], kind="stable")]            # the reference's stable sort by x (:110-111)
+    min_height = height - height // 10 if min_height is None else min_height
+    min_width = 0.65 * width if min_width is None else min_width
+    rows = rows[(rows[:, 2] > min_width) & (rows[:, 3] > min_height)]
+    top_bin = np.minimum(len(freqs) - 1, rows[:, 1] + rows[:, 3])
+    # seconds = frames * 281 / sr: the reference hard-codes 281 (not hop_length) and this operation order (:138-139)
+    signals = [signal_class(x * 281 / sr, (x + w) * 281 / sr, freqs[y], freqs[t], area)
+               for (x, y, w, _, area), t in zip(rows.tolist(), top_bin.tolist())]
     og_spec = restore(spec)
     return (signals, og_spec, debug) if return_debug else (signals, og_spec)
 
