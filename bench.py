@@ -191,6 +191,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
+    # stdout carries the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports NCCL_DEBUG) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = dist_.init()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -301,7 +303,33 @@ def run_ours(args):
                "api": "HostPipe.run (cacfe_hostpipe_run): pinned host -> H2D -> normalise/STFT/mel/PCEN -> D2H; "
                       f"{n_pipes} pipes on {n_pipes} host threads, each step copies its own batch in and out",
                "checksum": float(h_out[0][0, :4, :4].sum())}
-        del pipes, h_in, h_out
+        del pipes
+        if rank == 0 and world == 1:
+            # What the host link gives for exactly these two buffers (one batch up, one batch of features down, issued
+            # together on two streams; plumbing only, no kernels): the ceiling of any f32-in / f32-out end-to-end path.
+            d_up = torch.empty((B, CLIP), dtype=torch.float32, device=device)
+            d_dn = torch.ones((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, device=device)
+            s_up, s_dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+            def both():
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_in[0], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_out[0].copy_(d_dn, non_blocking=True)
+
+            both()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                both()
+            torch.cuda.synchronize()
+            t_link = (time.perf_counter() - t0) / 3
+            e2e["link_ceiling"] = {"clips_per_s": B / t_link, "frac": e2e["value"] / (B / t_link),
+                                   "h2d_GBps": B * CLIP * 4 / t_link / 1e9,
+                                   "note": "one batch's H2D and D2H issued together from pinned memory, no kernels "
+                                           "(tools/probe_pcie.py): the host link bounds e2e, not the GPU"}
+            del d_up, d_dn
+        del h_in, h_out
 
     # ---- the other HBM-bound rows of the path, timed alone on rank 0: not part of `value` ----------------
     rows = None
