@@ -15,9 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcacfe.so")
 SOURCES = ["cacfe.cu"]
-HEADERS = ["cacfe_common.cuh", "frontend_core.cuh", "fft64_gen.cuh", "k_frontend.cuh", "cacfe_async.cuh", "k_frontend_v3.cuh", "fft64x2_gen.cuh", "mel_jobs.h",
-           "k_melspec_tc.cuh", "k_sosfilt.cuh", "k_pcen.cuh",
-           "k_compress.cuh", "k_melspec.cuh", os.path.join("..", "..", "include", "cacfe.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "cacfe.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -31,8 +31,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // For waits that can last a large part of a tile (a group that runs ahead of the others): sleep between polls so the
 // spinning warps do not take issue slots from the warps they are waiting for.
+#ifndef CACFE_RELAXED_SLEEP_NS
+#define CACFE_RELAXED_SLEEP_NS 800
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(800);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(CACFE_RELAXED_SLEEP_NS);
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.w, p23.w, acc_b);
         };
         int i = 0;
+        // (measured alternative: the quad counts of the reference's bank (2 + 5 + 4) as a template parameter and this loop fully
+        // unrolled -- 96 fewer SASS instructions, no pointer / counter arithmetic -- 10.11 ms against 9.68 ms per 4096 clips:
+        // the scheduler hoists the 33 loads over the accumulate chains, spills more and the phase gets longer, not shorter.)
 #pragma unroll 1
         for (; i + 1 < nq; i += 2, wq += 128, pp += 4) {  // two quads per trip: six 16-byte loads in flight
           const float4 w0 = wq[0], a0 = pp[0], a1 = pp[1], w1 = wq[64], b0 = pp[2], b1 = pp[3];

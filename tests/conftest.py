@@ -37,3 +37,14 @@ def clips(oracle, golden):
     assert float(np.sum(x, dtype=np.float64)) == float(golden["clips_checksum"][0]), \
         "synthetic generator drifted from the one the golden vectors were made with"
     return x
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_draws(request):
+    """Every test starts from the same torch seed (CPU and CUDA): a test that draws without its own generator sees the same
+    numbers in every run and in every order, so a pass here is a pass on the driver's box."""
+    import zlib
+
+    import torch
+    torch.manual_seed(zlib.crc32(request.node.name.encode()))
+    yield
