@@ -178,7 +178,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    args.emit(line)
     return 0
 
 
@@ -191,8 +191,6 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
-    # stdout carries the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports NCCL_DEBUG) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = dist_.init()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -386,7 +384,7 @@ def run_ours(args):
                            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "other_rows": rows, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "checksum": float(out[0, :4, :4].sum())}
-        print(json.dumps(line))
+        args.emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -405,6 +403,20 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rows", action="store_true", help="skip the standalone timing of the other HBM-bound rows")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: while the run lasts, file descriptor 1 points at stderr, so that anything a
+    # library prints there (NCCL's "NCCL version ..." banner is a plain printf when the box exports NCCL_DEBUG=VERSION) cannot
+    # land next to it; emit() puts the descriptor back for the one line.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)          # teardown chatter (process-group destruction) stays off stdout too
+
+    args.emit = emit
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
