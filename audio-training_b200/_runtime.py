@@ -153,13 +153,26 @@ class Plan:
             raise TypeError(f"{what}: float32 required, got {x.dtype}")
         return x if x.is_contiguous() else x.contiguous()
 
+    # The C ABI takes 1..65535 batch entries per call (grid.y).  The reference's callables accept any batch, the empty one
+    # included (tf.data hands out whatever the last partial batch holds): an empty batch returns an empty result of the right
+    # shape without a launch, and operators whose clips are independent split a larger batch into calls of MAX_BATCH.
+    MAX_BATCH = 65535
+
+    def _batched(self, B, call):
+        for b0 in range(0, B, self.MAX_BATCH):
+            call(b0, min(self.MAX_BATCH, B - b0))
+
     def normalize(self, x):
         x = self._check_in(x, "normalize")
         n = x.shape[-1]
         rows = x.numel() // n
         out = torch.empty_like(x)
-        ws = self.workspace_for(rows)
-        _lib.check(self._lib.cacfe_normalize(self._handle, _ptr(x), _ptr(out), rows, n, _ptr(ws), _stream(self.device)))
+        if x.numel() == 0:
+            return out
+        ws = self.workspace_for(min(rows, self.MAX_BATCH))
+        xf, of = x.view(rows, n), out.view(rows, n)
+        self._batched(rows, lambda b0, nb: _lib.check(self._lib.cacfe_normalize(
+            self._handle, _ptr(xf[b0:b0 + nb]), _ptr(of[b0:b0 + nb]), nb, n, _ptr(ws), _stream(self.device))))
         return out
 
     def frontend(self, raw, out=None):
@@ -169,8 +182,11 @@ class Plan:
         B = raw.shape[0]
         if out is None:
             out = torch.empty(self.feature_shape(B), dtype=torch.float32, device=raw.device)
-        ws = self.workspace_for(B)
-        _lib.check(self._lib.cacfe_frontend(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
+        if B == 0:
+            return out
+        ws = self.workspace_for(min(B, self.MAX_BATCH))
+        self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_frontend(
+            self._handle, _ptr(raw[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, _ptr(ws), _stream(self.device))))
         return out
 
     def frontend_pcen(self, raw, params=None, out=None):
@@ -178,6 +194,8 @@ class Plan:
         B = raw.shape[0]
         if out is None:
             out = torch.empty((B, self.n_frames, self.config.n_mels), dtype=torch.float32, device=raw.device)
+        if B == 0:
+            return out
         ws = self.workspace_for(B)
         params = params or pcen_params()
         _lib.check(self._lib.cacfe_frontend_pcen(self._handle, ctypes.byref(params), _ptr(raw), _ptr(out), B, _ptr(ws),
@@ -192,6 +210,8 @@ class Plan:
             raise ValueError(f"stft: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
         B = raw.shape[0]
         out = torch.empty((B, self.n_bins, self.n_frames), dtype=torch.float32, device=raw.device)
+        if B == 0:
+            return out
         ws = self.workspace(self._lib.cacfe_stft_workspace_bytes(self._handle, B))
         _lib.check(self._lib.cacfe_stft(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
         return out
@@ -214,21 +234,28 @@ class Plan:
         c = self.config
         shape = (B, T, c.n_mels) if c.out_layout == "btm" else (B, c.n_mels, T, c.channels)
         out = torch.empty(shape, dtype=torch.float32, device=spec.device)
-        _lib.check(self._lib.cacfe_mel_from_spectrogram(self._handle, _ptr(spec), _ptr(out), B, T, _stream(self.device)))
+        if spec.numel() == 0:
+            return out
+        self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_mel_from_spectrogram(
+            self._handle, _ptr(spec[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, T, _stream(self.device))))
         return out
 
     def ema(self, x, smooth, time_axis=1):
         x = self._check_in(x, "ema")
         B, opc, T, inner = _split_axes(x, time_axis)
         out = torch.empty_like(x)
-        _lib.check(self._lib.cacfe_ema(self._handle, float(smooth), _ptr(x), _ptr(out), B, opc, T, inner,
-                                       _stream(self.device)))
+        if x.numel() == 0:
+            return out
+        self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_ema(
+            self._handle, float(smooth), _ptr(x[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, opc, T, inner, _stream(self.device))))
         return out
 
     def pcen(self, x, params=None, time_axis=1):
         x = self._check_in(x, "pcen")
         B, opc, T, inner = _split_axes(x, time_axis)
         out = torch.empty_like(x)
+        if x.numel() == 0:
+            return out
         params = params or pcen_params()
         ws = self.workspace(self._lib.cacfe_pcen_workspace_bytes(B, opc, inner))
         _lib.check(self._lib.cacfe_pcen(self._handle, ctypes.byref(params), _ptr(x), _ptr(out), B, opc, T, inner,
@@ -287,6 +314,8 @@ class Plan:
         if one.shape != two.shape or lam.numel() != one.shape[0]:
             raise ValueError("mix_up: shapes of the two batches / of lambda do not match")
         out = torch.empty_like(one)
+        if one.numel() == 0:
+            return out
         B = one.shape[0]
         _lib.check(self._lib.cacfe_mix_up(self._handle, _ptr(one), _ptr(two), _ptr(lam), _ptr(out), B, one.numel() // B,
                                           _stream(self.device)))
@@ -297,6 +326,8 @@ class Plan:
         entries = x.shape[0] if per_clip else 1
         per_entry = x.numel() // entries
         out = torch.empty_like(x)
+        if x.numel() == 0:
+            return out
         ws = self.workspace(self._lib.cacfe_compress_workspace_bytes(entries, per_entry))
         _lib.check(self._lib.cacfe_compress(self._handle, _COMPRESS[mode], float(param), _ptr(x), _ptr(out), entries,
                                             per_entry, _ptr(ws), _stream(self.device)))

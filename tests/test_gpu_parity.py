@@ -589,6 +589,45 @@ def test_errors():
     assert plan.launch_count() >= 0
 
 
+def test_empty_batches():
+    """The reference's callables accept an empty batch (tf.data hands over whatever the last partial batch holds; load_samples
+    of a recording without tracks returns []): every operator returns an empty result of the right shape, no launch."""
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=3, out_layout="bmtc"), 0)
+    n0 = plan.launch_count()
+    raw = torch.zeros((0, 144000), device="cuda")
+    assert tuple(plan.frontend(raw).shape) == (0, 160, 513, 3)
+    assert tuple(plan.normalize(raw).shape) == (0, 144000)
+    assert tuple(plan.stft(raw).shape) == (0, plan.n_bins, 513)
+    btm = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
+    assert tuple(btm.frontend_pcen(raw).shape) == (0, 513, 160)
+    feat = torch.zeros((0, 513, 160), device="cuda")
+    assert tuple(btm.pcen(feat).shape) == (0, 513, 160)
+    assert tuple(btm.ema(feat, 0.04).shape) == (0, 513, 160)
+    assert tuple(btm.compress(feat, "minmax").shape) == (0, 513, 160)
+    assert tuple(btm.mel_from_spectrogram(torch.zeros((0, btm.n_bins, 513), device="cuda")).shape) == (0, 513, 160)
+    img, y = td.raw_to_mel(raw, "labels")
+    assert tuple(img.shape) == (0, 160, 513, 3) and y == "labels"
+    assert plan.launch_count() == n0 and btm.launch_count() >= 0
+    from audio_training_b200 import predict_utils as pu
+    assert pu.load_samples(np.zeros(48000 * 5, np.float32), 48000, []) == []
+
+
+def test_batches_beyond_one_launch(oracle):
+    """More batch entries than one launch takes (65535): operators whose entries are independent are split by the host
+    mirror, with the same results as the oracle on every row."""
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    rng = np.random.default_rng(5)
+    x = rng.random((65535 + 70, 9, 2)).astype(np.float32)
+    got = plan.ema(torch.from_numpy(x).cuda(), 0.3).cpu().numpy()
+    want = oracle.ema(x[-80:], 0.3, np.float32)
+    assert np.array_equal(got[-80:], want)
+    assert np.array_equal(got[:40], oracle.ema(x[:40], 0.3, np.float32))
+    rows = rng.random((65535 + 33, 16)).astype(np.float32)
+    got = plan.normalize(torch.from_numpy(rows).cuda()).cpu().numpy()
+    assert np.array_equal(got[-40:], oracle.normalize(rows[-40:], np.float32))
+    assert np.array_equal(got[:40], oracle.normalize(rows[:40], np.float32))
+
+
 # ------------------------------------------------------------------------------------------------ PCEN backward (8f rank 4)
 @pytest.mark.parametrize("shape,axis,scope,kw", [
     ((3, 70, 40), 1, "tensor", {}),
