@@ -655,7 +655,7 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     float2* partial = (float2*)ws;
     float2* norm = (float2*)((char*)ws + align256((size_t)B * kMaxSplits * sizeof(float2)));
     cacfe::row_minmax_kernel<<<dim3(splits, B), 256, 0, st>>>(raw, p->cfg.n_samples, splits, partial);
-    cacfe::minmax_finalize_kernel<<<B, 32, 0, st>>>(partial, splits, norm);  // -> (max - min, min) per clip
+    cacfe::minmax_finalize_kernel<true><<<B, 32, 0, st>>>(partial, splits, norm);  // -> (max - min, min) per clip
     a.norm = norm;
     launches = 3;
   }
@@ -945,9 +945,9 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
     a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
     cacfe::pcen_scan_kernel<cacfe::PCEN_REDUCE><<<ctas, cacfe::kScanWarps * 32, smem, st>>>(a, rows, outer_per_clip);
     if (a.per_clip_extremes)
-      cacfe::minmax_finalize_kernel<<<B, 256, 0, st>>>(a.partial, (int)(outer_per_clip / cacfe::kScanWarps), ext);
+      cacfe::minmax_finalize_kernel<false><<<B, 256, 0, st>>>(a.partial, (int)(outer_per_clip / cacfe::kScanWarps), ext);
     else
-      cacfe::minmax_finalize_kernel<<<1, 256, 0, st>>>(a.partial, (int)ctas, ext);
+      cacfe::minmax_finalize_kernel<false><<<1, 256, 0, st>>>(a.partial, (int)ctas, ext);
     cacfe::pcen_scan_kernel<cacfe::PCEN_APPLY><<<ctas, cacfe::kScanWarps * 32, smem, st>>>(a, rows, outer_per_clip);
     return check_launch(p, "pcen (scan)", 3);
   }

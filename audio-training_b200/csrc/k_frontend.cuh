@@ -30,26 +30,26 @@ __global__ void __launch_bounds__(256) row_minmax_kernel(const float* __restrict
     for (; i + 3 * 256 < hi; i += 4 * 256) {  // 4 independent 16 B loads in flight per thread
       const float4 a = ld_stream4(x4 + i), b = ld_stream4(x4 + i + 256), c = ld_stream4(x4 + i + 512),
                    d = ld_stream4(x4 + i + 768);
-      mn = fminf(mn, fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))));
-      mn = fminf(mn, fminf(fminf(fminf(c.x, c.y), fminf(c.z, c.w)), fminf(fminf(d.x, d.y), fminf(d.z, d.w))));
-      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
-      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+      mn = min_nan(mn, min_nan(min_nan(min_nan(a.x, a.y), min_nan(a.z, a.w)), min_nan(min_nan(b.x, b.y), min_nan(b.z, b.w))));
+      mn = min_nan(mn, min_nan(min_nan(min_nan(c.x, c.y), min_nan(c.z, c.w)), min_nan(min_nan(d.x, d.y), min_nan(d.z, d.w))));
+      mx = max_nan(mx, max_nan(max_nan(max_nan(a.x, a.y), max_nan(a.z, a.w)), max_nan(max_nan(b.x, b.y), max_nan(b.z, b.w))));
+      mx = max_nan(mx, max_nan(max_nan(max_nan(c.x, c.y), max_nan(c.z, c.w)), max_nan(max_nan(d.x, d.y), max_nan(d.z, d.w))));
     }
     for (; i < hi; i += 256) {
       const float4 a = ld_stream4(x4 + i);
-      mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
-      mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      mn = min_nan(mn, min_nan(min_nan(a.x, a.y), min_nan(a.z, a.w)));
+      mx = max_nan(mx, max_nan(max_nan(a.x, a.y), max_nan(a.z, a.w)));
     }
   } else {
     const long long per = (n + splits - 1) / splits;
     const long long lo = per * blockIdx.x, hi = min(n, lo + per);
     for (long long i = lo + threadIdx.x; i < hi; i += 256) {
       const float v = x[i];
-      mn = fminf(mn, v);
-      mx = fmaxf(mx, v);
+      mn = min_nan(mn, v);
+      mx = max_nan(mx, v);
     }
   }
-  block_minmax(mn, mx, scratch);
+  block_minmax_nan(mn, mx, scratch);
   if (threadIdx.x == 0) partial[row * splits + blockIdx.x] = make_float2(mn, mx);
 }
 
@@ -59,8 +59,8 @@ __device__ __forceinline__ void fold_partials(const float2* __restrict__ partial
   mx = -INFINITY;
   for (int s = 0; s < splits; ++s) {
     const float2 p = partial[row * splits + s];
-    mn = fminf(mn, p.x);
-    mx = fmaxf(mx, p.y);
+    mn = min_nan(mn, p.x);
+    mx = max_nan(mx, p.y);
   }
 }
 

@@ -53,10 +53,10 @@ __global__ void __cluster_dims__(kNcCluster, 1, 1) __launch_bounds__(kNcThreads)
   float mn = INFINITY, mx = -INFINITY;
   for (int i = tid; i < n4; i += kNcThreads) {
     const float4 v = s4[i];
-    mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    mn = min_nan(mn, min_nan(min_nan(v.x, v.y), min_nan(v.z, v.w)));
+    mx = max_nan(mx, max_nan(max_nan(v.x, v.y), max_nan(v.z, v.w)));
   }
-  block_minmax(mn, mx, scratch);
+  block_minmax_nan(mn, mx, scratch);
   if (tid == 0) s_mm = make_float2(mn, mx);
   cluster.sync();
   if (tid < 32) {
@@ -66,8 +66,8 @@ __global__ void __cluster_dims__(kNcCluster, 1, 1) __launch_bounds__(kNcThreads)
       a = v.x;
       b = v.y;
     }
-    a = warp_min(a);
-    b = warp_max(b);
+    a = warp_min_nan(a);
+    b = warp_max_nan(b);
     if (tid == 0) s_all = make_float2(a, b);
   }
   cluster.sync();   // nobody leaves (or overwrites s_mm) while a peer may still be reading it

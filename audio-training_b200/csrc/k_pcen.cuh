@@ -105,16 +105,19 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
 }
 
 // Fold block partials into (range, min) per scope entry.  grid = entries, block = 256.
+// NANP: NaN-propagating fold (the clip normalisation: numpy semantics, a NaN sample makes the clip's range NaN).
+template <bool NANP = false>
 __global__ void __launch_bounds__(256) minmax_finalize_kernel(const float2* __restrict__ partial, int per_entry,
                                                               float2* __restrict__ extremes) {
   __shared__ float scratch[64];
   const float2* p = partial + (size_t)blockIdx.x * per_entry;
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < per_entry; i += blockDim.x) {
-    mn = fminf(mn, p[i].x);
-    mx = fmaxf(mx, p[i].y);
+    mn = NANP ? min_nan(mn, p[i].x) : fminf(mn, p[i].x);
+    mx = NANP ? max_nan(mx, p[i].y) : fmaxf(mx, p[i].y);
   }
-  block_minmax(mn, mx, scratch);
+  if (NANP) block_minmax_nan(mn, mx, scratch);
+  else block_minmax(mn, mx, scratch);
   if (threadIdx.x == 0) extremes[blockIdx.x] = make_float2(mx - mn, mn);  // (range, min)
 }
 

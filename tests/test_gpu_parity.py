@@ -218,6 +218,27 @@ def test_constant_clip_is_nan_through_fused_path(oracle):
     assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
 
 
+def test_nan_sample_poisons_its_clip_only(oracle):
+    """np.min / np.max (predict_utils.normalize_data, predict_utils.py:153-160) propagate NaN: one NaN sample makes the whole
+    clip NaN after the normalisation, hence every feature of that clip; its batch-mates are untouched.  (fminf / fmaxf would
+    skip the NaN and poison only the frames that cover it.)"""
+    x = oracle.synth_clips(np.arange(3))
+    x[1, 70001] = np.nan
+    dev = torch.from_numpy(x).cuda()
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1), 0)
+    want = oracle.normalize(x, np.float32)
+    assert np.isnan(want[1]).all()
+    for forced in (False, True):                      # cluster kernel, then the two-kernel path
+        plan.force_generic(forced)
+        got = plan.normalize(dev).cpu().numpy()
+        plan.force_generic(False)
+        assert np.isnan(got[1]).all()
+        assert np.array_equal(got[[0, 2]], want[[0, 2]])
+    out = plan.frontend(dev)
+    assert torch.isnan(out[1]).all()
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+
+
 # ------------------------------------------------------------------------------------------------ path B
 @pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
 def test_path_b(oracle, golden, xn, pad_mode):
