@@ -85,6 +85,8 @@ PROTOTYPES = {
     "cacfe_hostpipe_destroy": (None, [c_void_p]),
     "cacfe_hostpipe_run": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int]),
     "cacfe_hostpipe_device_bytes": (c_size_t, [c_void_p]),
+    "cacfe_hostpipe_run_pcm16": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int]),
+    "cacfe_pcm16_to_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "cacfe_host_register": (c_int, [c_void_p, c_size_t]),
     "cacfe_host_unregister": (c_int, [c_void_p]),
     "cacfe_frontend_dlpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

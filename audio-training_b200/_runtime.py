@@ -306,6 +306,16 @@ class Plan:
             return stats, {"mask": mask, "raw_mask": raw, "row_medians": rm, "column_medians": cm}
         return stats
 
+    def pcm16_to_f32(self, pcm):
+        """int16 PCM (CUDA tensor) -> float32 samples s / 32768: what soundfile / librosa.load return for a 16-bit file."""
+        if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda and pcm.dtype == torch.int16):
+            raise TypeError("pcm16_to_f32: CUDA int16 tensor required")
+        pcm = pcm if pcm.is_contiguous() else pcm.contiguous()
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        if pcm.numel():
+            _lib.check(self._lib.cacfe_pcm16_to_f32(self._handle, _ptr(pcm), _ptr(out), pcm.numel(), _stream(self.device)))
+        return out
+
     def mix_up(self, one, two, lam):
         """one * lam[b] + two * (1 - lam[b]) per batch entry (tfdataset.py:948)."""
         one = self._check_in(one, "mix_up")
@@ -373,12 +383,16 @@ class HostPipe:
         return int(self._lib.cacfe_hostpipe_device_bytes(self._handle))
 
     def run(self, host_in, host_out=None, params=None):
-        """host_in: float32 [B, n_samples] numpy array or CPU tensor (pinned for full PCIe rate).
+        """host_in: float32 [B, n_samples] numpy array or CPU tensor (pinned for full PCIe rate) -- or int16 PCM of the same
+        shape (extension): uploaded as 16-bit samples and converted on the device as s / 32768, the float32 values soundfile /
+        librosa.load give for a 16-bit file, so the features equal those of the float32 call bit for bit at half the upload.
         params=None -> mel image in the plan's layout; PcenParams -> PCEN output [B, T, n_mels]."""
         is_np = isinstance(host_in, np.ndarray)
         tin = torch.from_numpy(host_in) if is_np else host_in
-        if tin.is_cuda or tin.dtype != torch.float32 or not tin.is_contiguous():
-            raise TypeError("HostPipe.run: contiguous float32 host buffer required")
+        if tin.is_cuda or tin.dtype not in (torch.float32, torch.int16) or not tin.is_contiguous():
+            raise TypeError("HostPipe.run: contiguous float32 (or int16 PCM) host buffer required")
+        if tin.dim() != 2 or tin.shape[1] != self.plan.config.n_samples:
+            raise ValueError(f"HostPipe.run: expected [B, {self.plan.config.n_samples}], got {tuple(tin.shape)}")
         B = tin.shape[0]
         c = self.plan.config
         shape = (B, self.plan.n_frames, c.n_mels) if params is not None else self.plan.feature_shape(B)
@@ -388,8 +402,9 @@ class HostPipe:
             tout = torch.from_numpy(host_out) if isinstance(host_out, np.ndarray) else host_out
             if tuple(tout.shape) != tuple(shape) or tout.dtype != torch.float32 or not tout.is_contiguous():
                 raise ValueError(f"HostPipe.run: host_out must be contiguous float32 {shape}")
-        _lib.check(self._lib.cacfe_hostpipe_run(self._handle, ctypes.byref(params) if params is not None else None,
-                                                ctypes.c_void_p(tin.data_ptr()), ctypes.c_void_p(tout.data_ptr()), B))
+        entry = self._lib.cacfe_hostpipe_run_pcm16 if tin.dtype == torch.int16 else self._lib.cacfe_hostpipe_run
+        _lib.check(entry(self._handle, ctypes.byref(params) if params is not None else None,
+                         ctypes.c_void_p(tin.data_ptr()), ctypes.c_void_p(tout.data_ptr()), B))
         if host_out is not None:
             return host_out
         return tout.numpy() if is_np else tout

@@ -1253,6 +1253,7 @@ struct cacfe_hostpipe {
   cudaEvent_t done[2] = {nullptr, nullptr};
   cudaEvent_t all_reduced = nullptr;
   float* d_in[2] = {nullptr, nullptr};   // [chunk][n_samples]
+  short* d_in16[2] = {nullptr, nullptr};  // [chunk][n_samples] 16-bit PCM staging, allocated by the first cacfe_hostpipe_run_pcm16
   float* d_feat = nullptr;               // [max_B] mel features (layout of the run)
   float* d_out[2] = {nullptr, nullptr};  // [chunk] PCEN output staging
   void* d_ws[2] = {nullptr, nullptr};    // per-stream front-end workspace
@@ -1269,6 +1270,7 @@ void cacfe_hostpipe_destroy(cacfe_hostpipe* h) {
   for (int i = 0; i < 2; ++i) {
     if (h->stream[i]) cudaStreamSynchronize(h->stream[i]);
     cudaFree(h->d_in[i]);
+    cudaFree(h->d_in16[i]);
     cudaFree(h->d_out[i]);
     cudaFree(h->d_ws[i]);
     if (h->done[i]) cudaEventDestroy(h->done[i]);
@@ -1321,21 +1323,48 @@ int cacfe_hostpipe_create(cacfe_plan* p, int max_B, int chunk, cacfe_hostpipe** 
 
 size_t cacfe_hostpipe_device_bytes(const cacfe_hostpipe* h) { return h ? h->bytes : 0; }
 
-int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const float* host_in, float* host_out, int B) {
-  if (!h || !host_in || !host_out) return fail(CACFE_EINVAL, "hostpipe_run: null argument");
+}  // extern "C"
+
+// One body for both host formats: `host_in` (float32) or `host_pcm` (16-bit PCM, converted on the device as s / 32768 -- what
+// soundfile / librosa.load return for a 16-bit file, audiowriter.py:352 -- so that the features are bit-identical to the
+// float32 call on the converted samples while the upload moves half the bytes).
+static int hostpipe_run_impl(cacfe_hostpipe* h, const cacfe_pcen_params* q, const float* host_in, const short* host_pcm,
+                             float* host_out, int B) {
+  if (!h || (!host_in && !host_pcm) || !host_out) return fail(CACFE_EINVAL, "hostpipe_run: null argument");
   if (B < 1 || B > h->max_B) return fail(CACFE_ESHAPE, "hostpipe_run: B=%d exceeds max_B=%d", B, h->max_B);
   cacfe_plan* p = h->plan;
   CUDA_TRY(cudaSetDevice(p->device));
   const int ns = p->cfg.n_samples;
   const int nchunks = (B + h->chunk - 1) / h->chunk;
+  if (host_pcm) {
+    for (int i = 0; i < 2; ++i)
+      if (!h->d_in16[i]) {
+        const size_t bytes = (size_t)h->chunk * ns * sizeof(short);
+        cudaError_t e = cudaMalloc((void**)&h->d_in16[i], bytes);
+        if (e != cudaSuccess)
+          return fail(e == cudaErrorMemoryAllocation ? CACFE_ENOMEM : CACFE_ECUDA, "hostpipe_run_pcm16: %s", cudaGetErrorString(e));
+        h->bytes += bytes;
+      }
+  }
+  // chunk b0.. of the caller's buffer -> d_in[s] on stream st
+  auto upload = [&](int s, int b0, int nb, cudaStream_t st) -> cudaError_t {
+    if (!host_pcm)
+      return cudaMemcpyAsync(h->d_in[s], host_in + (size_t)b0 * ns, (size_t)nb * ns * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(h->d_in16[s], host_pcm + (size_t)b0 * ns, (size_t)nb * ns * sizeof(short),
+                                    cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    const long long n = (long long)nb * ns;
+    cacfe::pcm16_to_f32_kernel<<<(unsigned)std::min<long long>((n / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(h->d_in16[s], h->d_in[s], n);
+    p->launches.fetch_add(1);
+    return cudaGetLastError();
+  };
   if (q == nullptr) {
     // mel image only: every chunk is independent -> H2D / kernels / D2H fully pipelined on two streams
     const size_t feat_clip = (size_t)p->n_frames * p->cfg.n_mels * p->cfg.channels;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
       cudaStream_t st = h->stream[s];
-      CUDA_TRY(cudaMemcpyAsync(h->d_in[s], host_in + (size_t)b0 * ns, (size_t)nb * ns * sizeof(float),
-                               cudaMemcpyHostToDevice, st));
+      CUDA_TRY(upload(s, b0, nb, st));
       float* feat = h->d_feat + (size_t)b0 * feat_clip;
       int rc = launch_frontend(p, h->d_in[s], feat, nb, p->cfg.out_layout, p->cfg.channels, h->d_ws[s], st,
                                (float*)((char*)h->d_ws[s] + frontend_ws_bytes(h->chunk)));
@@ -1370,8 +1399,7 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1, b0 = c * h->chunk, nb = (B - b0 < h->chunk) ? B - b0 : h->chunk;
     cudaStream_t st = h->stream[s];
-    CUDA_TRY(cudaMemcpyAsync(h->d_in[s], host_in + (size_t)b0 * ns, (size_t)nb * ns * sizeof(float),
-                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(upload(s, b0, nb, st));
     float* mel = h->d_feat + (size_t)b0 * clip;
     rc = launch_frontend(p, h->d_in[s], mel, nb, CACFE_LAYOUT_BTM, 1, h->d_ws[s], st);
     if (rc != CACFE_OK) return rc;
@@ -1424,6 +1452,26 @@ int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const floa
   CUDA_TRY(cudaStreamSynchronize(h->stream[0]));
   CUDA_TRY(cudaStreamSynchronize(h->stream[1]));
   return CACFE_OK;
+}
+
+extern "C" {
+
+int cacfe_hostpipe_run(cacfe_hostpipe* h, const cacfe_pcen_params* q, const float* host_in, float* host_out, int B) {
+  return hostpipe_run_impl(h, q, host_in, nullptr, host_out, B);
+}
+
+int cacfe_hostpipe_run_pcm16(cacfe_hostpipe* h, const cacfe_pcen_params* q, const int16_t* host_pcm, float* host_out, int B) {
+  if (!host_pcm) return fail(CACFE_EINVAL, "hostpipe_run_pcm16: null argument");
+  return hostpipe_run_impl(h, q, nullptr, reinterpret_cast<const short*>(host_pcm), host_out, B);
+}
+
+int cacfe_pcm16_to_f32(cacfe_plan* p, const int16_t* in_dev, float* out_dev, long long n, void* stream) {
+  if (!p || !in_dev || !out_dev) return fail(CACFE_EINVAL, "pcm16_to_f32: null argument");
+  if (n < 1) return fail(CACFE_ESHAPE, "pcm16_to_f32: n=%lld", n);
+  CUDA_TRY(cudaSetDevice(p->device));
+  cacfe::pcm16_to_f32_kernel<<<(unsigned)std::min<long long>((n / 8 + 255) / 256 + 1, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const short*>(in_dev), out_dev, n);
+  return check_launch(p, "pcm16_to_f32", 1);
 }
 
 int cacfe_host_register(void* ptr, size_t bytes) {

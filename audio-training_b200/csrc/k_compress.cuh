@@ -166,4 +166,22 @@ __global__ void __launch_bounds__(256) mix_up_kernel(const float* __restrict__ o
   }
 }
 
+// 16-bit PCM -> float32, the conversion libsndfile / soundfile / librosa.load apply to a 16-bit file: s / 32768 (exact in
+// FP32).  16-byte loads of eight samples, two 16-byte stores; a scalar tail for lengths that are not a multiple of 8.
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long n8 = (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) ? n >> 3 : 0;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const int4* in8 = reinterpret_cast<const int4*>(in);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  constexpr float k = 1.0f / 32768.0f;
+  for (long long i = first; i < n8; i += stride) {
+    const int4 v = __ldcs(in8 + i);
+    auto lo = [](int w) { return (float)(short)(w & 0xffff) * k; };
+    auto hi = [](int w) { return (float)(w >> 16) * k; };
+    out4[2 * i] = make_float4(lo(v.x), hi(v.x), lo(v.y), hi(v.y));       // read again right away by K0 / K1: plain stores
+    out4[2 * i + 1] = make_float4(lo(v.z), hi(v.z), lo(v.w), hi(v.w));
+  }
+  for (long long i = (n8 << 3) + first; i < n; i += stride) out[i] = (float)in[i] * k;
+}
+
 }  // namespace cacfe

@@ -210,6 +210,15 @@ void cacfe_hostpipe_destroy(cacfe_hostpipe* pipe);
  * host_in [B][n_samples], host_out sized accordingly; both should be page-locked (cacfe_host_register).
  * Synchronous: returns when host_out is complete. */
 int cacfe_hostpipe_run(cacfe_hostpipe* pipe, const cacfe_pcen_params* params, const float* host_in, float* host_out, int B);
+/* The same run from 16-bit PCM host samples [B][n_samples] (extension: the reference's callables take float32 only).  The
+ * decoders the reference reads its audio with (librosa.load -> soundfile, audiowriter.py:352,497, audiosplitter.py:20) turn a
+ * 16-bit file into float32 as s / 32768; this entry uploads the 16-bit samples (half the bytes of the float32 upload, which is
+ * what bounds the host path) and applies that conversion on the device, so the features are bit-identical to
+ * cacfe_hostpipe_run on the converted samples.  The staging for it is allocated by the first call. */
+int cacfe_hostpipe_run_pcm16(cacfe_hostpipe* pipe, const cacfe_pcen_params* params, const int16_t* host_pcm, float* host_out,
+                             int B);
+/* Device form of the conversion: out_dev[i] = in_dev[i] / 32768 for n samples. */
+int cacfe_pcm16_to_f32(cacfe_plan* plan, const int16_t* in_dev, float* out_dev, long long n, void* stream);
 size_t cacfe_hostpipe_device_bytes(const cacfe_hostpipe* pipe);
 int cacfe_host_register(void* ptr, size_t bytes);
 int cacfe_host_unregister(void* ptr);

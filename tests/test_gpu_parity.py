@@ -610,6 +610,28 @@ def test_errors():
     assert plan.launch_count() >= 0
 
 
+def test_hostpipe_pcm16_is_bit_identical_to_float32(oracle):
+    """cacfe_hostpipe_run_pcm16: 16-bit PCM up, s / 32768 on the device (what soundfile / librosa.load return for a 16-bit
+    file) -- the same features, bit for bit, as the float32 call on the converted samples; and the device form of the
+    conversion, unaligned tail included."""
+    x = oracle.synth_clips(np.arange(5))
+    pcm = np.clip(np.round(x / np.abs(x).max() * 30000.0), -32768, 32767).astype(np.int16)
+    f32 = pcm.astype(np.float32) / np.float32(32768.0)
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
+    pipe = rt.HostPipe(plan, max_B=5, chunk=2)                       # 3 chunks, the last one partial
+    for params in (rt.pcen_params(), rt.pcen_params(norm_scope="clip"), None):
+        a = pipe.run(torch.from_numpy(pcm).pin_memory(), params=params)
+        b = pipe.run(torch.from_numpy(f32).pin_memory(), params=params)
+        assert torch.equal(a, b)
+        assert torch.isfinite(a).all()
+    dev = torch.from_numpy(pcm).cuda()
+    assert np.array_equal(plan.pcm16_to_f32(dev).cpu().numpy(), f32)
+    flat = dev.reshape(-1)[3:3 + 100003]                             # 2-byte aligned start, length not a multiple of 8
+    assert np.array_equal(plan.pcm16_to_f32(flat).cpu().numpy(), f32.reshape(-1)[3:3 + 100003])
+    with pytest.raises(TypeError):
+        pipe.run(torch.zeros((2, 144000), dtype=torch.float64))
+
+
 def test_empty_batches():
     """The reference's callables accept an empty batch (tf.data hands over whatever the last partial batch holds; load_samples
     of a recording without tracks returns []): every operator returns an empty result of the right shape, no launch."""
