@@ -92,7 +92,13 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   int* s_done = reinterpret_cast<int*>(s_full + 6);                   // [2] groups that have read the tile
   float2* s_nrm = reinterpret_cast<float2*>(s_full + 8);              // [2][2] (range, min) of clips b & ~1, b | 1
 
+#ifdef CACFE_K1_WARP_PERM   // A/B switch (tools/ab_k1.py): put both warps of FFT groups 0..3 on one scheduler (warps w, w + 4)
+  const int pw_ = (int)(threadIdx.x >> 5);
+  const int lw_ = pw_ < 8 ? ((pw_ & 3) * 2 + (pw_ >> 2)) : pw_;
+  const int tid = lw_ * 32 + (int)(threadIdx.x & 31);
+#else
   const int tid = threadIdx.x;
+#endif
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int g = tid >> 6, t64 = tid & 63, lane = tid & 31;
 
