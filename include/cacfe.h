@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CACFE_VERSION 100 /* 0.1.0 */
+#define CACFE_VERSION 101 /* 0.1.1: + cacfe_hostpipe_run_pcm16, cacfe_pcm16_to_f32 */
 
 typedef enum cacfe_status {
   CACFE_OK = 0,
