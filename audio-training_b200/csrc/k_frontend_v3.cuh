@@ -32,7 +32,10 @@
 
 namespace cacfe {
 
-constexpr int kVGroups = 6;
+#ifndef CACFE_VGROUPS          // FFT groups (64 threads each) per CTA; a tile is 2 * groups frames.  A/B switch: tools/ab_k1.py
+#define CACFE_VGROUPS 6
+#endif
+constexpr int kVGroups = CACFE_VGROUPS;
 constexpr int kHalfStride = 68;                    // floats per half-exchange row: 272 B = 2*128 + 16
 constexpr int kHalfFloats = 64 * kHalfStride;      // 17408 B per group
 constexpr int kVThreads = kVGroups * 64;
