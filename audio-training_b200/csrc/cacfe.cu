@@ -953,8 +953,18 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
   }
   const PcenGrid g = pcen_grid(a.rows_per_clip);
   dim3 grid(g.gx, B);
+  static const int dyn = [] {   // residency probe (tools/probe_pcen_waves.py --residency): unused dynamic shared memory per block
+    const char* e = getenv("CACFE_PCEN_DYN_SMEM");
+    const int v = e ? atoi(e) : 0;
+    if (v > 0) {
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    }
+    return v;
+  }();
   if (q->norm_scope == CACFE_NORM_NONE) {
-    cacfe::pcen_kernel<cacfe::PCEN_RAW><<<grid, g.block, 0, st>>>(a);
+    cacfe::pcen_kernel<cacfe::PCEN_RAW><<<grid, g.block, dyn, st>>>(a);
     return check_launch(p, "pcen");
   }
   if (!ws) return fail(CACFE_EINVAL, "pcen: workspace required for the min-max scope");
@@ -963,12 +973,12 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
   a.partial = partial;
   a.extremes = extremes;
   a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
-  cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<grid, g.block, 0, st>>>(a);
+  cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<grid, g.block, dyn, st>>>(a);
   if (a.per_clip_extremes)
     cacfe::pcen_extremes_kernel<<<B, 256, 0, st>>>(partial, g.gx, extremes, a, 0);
   else
     cacfe::pcen_extremes_kernel<<<1, 256, 0, st>>>(partial, B * g.gx, extremes, a, 0);
-  cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<grid, g.block, 0, st>>>(a);
+  cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<grid, g.block, dyn, st>>>(a);
   return check_launch(p, "pcen", 3);
 }
 
