@@ -49,7 +49,7 @@ __device__ __forceinline__ float pcen_root(float y, const PcenArgs& a) {
 __device__ __forceinline__ float pcen_point(float x, float m, const PcenArgs& a) { return pcen_root(pcen_y(x, m, a), a); }
 
 // Loads in flight per lane.  Measured on [4096, 513, 160], both passes of the tensor-global scope (tools/probe_pcen_waves.py,
-// results bit-identical): 8 -> 0.811 ms, 12 -> 0.821, 16 -> 0.778, 24 -> 0.776, 32 -> 0.752.  The passes are latency-bound
+// results bit-identical): 8 -> 0.811 ms, 12 -> 0.821, 16 -> 0.778, 24 -> 0.776, 32 -> 0.752, 48 -> 0.868, 64 -> 0.895.  The passes are latency-bound
 // (capping the resident blocks per SM to make the rounds of a launch come out even only slows them down: 0.81 -> 1.21 ms from
 // 12 down to 4 blocks), so bytes in flight per lane are what pays.  ema_kernel keeps its own double-buffered batch of 8.
 #ifndef CACFE_PCEN_UNROLL
