@@ -7,7 +7,7 @@
 //   reference contract [B, T, F]        -> outer = B,       inner = F   (lanes across F: coalesced rows)
 //   image layout       [B, M, T, C] (*) -> outer = B * M,   inner = C   (* our rank-4 extension)
 // Each thread owns one (outer, inner) lane and walks T sequentially -- the reference's exact EMA order --
-// with kUnroll independent loads in flight.  HBM bound: 1 read (+1 write) of 4 B per element and pass.
+// with kPcenUnroll (32) independent loads in flight.  HBM bound: 1 read (+1 write) of 4 B per element and pass.
 //
 // The tensor-global min/max (Q14) is a grid-wide dependency, so the op is two passes over the *input*:
 //   pass REDUCE : PCEN in registers, block (min, max) partials only            (reads 4 B / element)
