@@ -14,6 +14,9 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcacfe.so")
+# the same library built with -DCACFE_K1_JITTER: random pauses before every hand-over of the persistent fused kernels.  Test
+# infrastructure (tests/test_gpu_parity.py::test_k1_jitter loads it in a child process); the product never loads it.
+JITTER_LIB_PATH = os.path.join(HERE, "libcacfe_jitter.so")
 SOURCES = ["cacfe.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "cacfe.h")]
 
@@ -61,6 +64,7 @@ PROTOTYPES = {
     "cacfe_plan_launch_count": (c_longlong, [c_void_p]),
     "cacfe_plan_profile": (c_int, [c_void_p, c_int]),
     "cacfe_plan_force_generic": (c_int, [c_void_p, c_int]),
+    "cacfe_plan_select_kernel": (c_int, [c_void_p, c_int]),
     "cacfe_plan_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "cacfe_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]),
     "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
@@ -104,25 +108,33 @@ _lock = threading.Lock()
 _lib = None
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
+def needs_build(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    built = os.path.getmtime(LIB_PATH)
+    built = os.path.getmtime(path)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> audio-training_b200/libcacfe.so"""
-    if not force and not needs_build():
-        return LIB_PATH
+def build(force=False, verbose=False, jitter=True):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> audio-training_b200/libcacfe.so, and (jitter=True)
+    the -DCACFE_K1_JITTER build next to it; the two compilations run side by side."""
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    jobs = []
+    for path, extra in ((LIB_PATH, []), (JITTER_LIB_PATH, ["-DCACFE_K1_JITTER"])):
+        if path == JITTER_LIB_PATH and not jitter:
+            continue
+        if not force and not needs_build(path):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", path] + SOURCES
+        jobs.append((path, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for path, proc in jobs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {os.path.basename(path)}:\n" + out + err)
+        if verbose:
+            print(err)
     return LIB_PATH
 
 

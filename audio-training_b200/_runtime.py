@@ -59,7 +59,14 @@ def pcen_params(gain=0.98, bias=2.0, root=2.0, smooth=0.04, eps=1e-6, norm_scope
 
 
 class Plan:
-    """A cacfe_plan plus its (growing) device workspace.  One per (config, device, filterbank)."""
+    """A cacfe_plan plus its (growing) device workspaces.  One per (config, device, filterbank).
+
+    Thread-safety contract (include/cacfe.h: "a plan is immutable after creation and may be shared between threads
+    provided each concurrent call uses its own workspace and stream"): the C entries are multi-launch sequences that
+    pass per-clip statistics through the workspace, and ctypes releases the GIL during a call, so the workspace is
+    kept per (calling thread, CUDA stream).  Any number of threads -- the tf.data `num_parallel_calls` pattern these
+    drop-ins replace -- may call the operators of one cached plan concurrently, on the same or on different streams;
+    two calls of ONE thread on ONE stream are ordered by the stream and share a buffer."""
 
     def __init__(self, config: FrontendConfig, device: int = 0, filterbank: np.ndarray | None = None):
         lib = _lib.load()
@@ -67,7 +74,7 @@ class Plan:
         self.device = int(device)
         self._lib = lib
         self._handle = ctypes.c_void_p(0)
-        self._ws = None
+        self._ws = {}                      # (thread id, stream handle) -> uint8 device tensor
         self._ws_lock = threading.Lock()
         cfg = Config()
         cfg.sr, cfg.n_samples, cfg.n_fft, cfg.hop = config.sr, config.n_samples, config.n_fft, config.hop
@@ -118,6 +125,10 @@ class Plan:
         """Use the generic (non-streaming) fused kernel even where the TMA streaming form applies."""
         _lib.check(self._lib.cacfe_plan_force_generic(self._handle, 1 if enable else 0))
 
+    def select_kernel(self, which=0):
+        """0: the newest persistent fused kernel that applies (stft_mel_v4_kernel); 3: stft_mel_v3_kernel."""
+        _lib.check(self._lib.cacfe_plan_select_kernel(self._handle, int(which)))
+
     def profile(self, enable=True):
         _lib.check(self._lib.cacfe_plan_profile(self._handle, 1 if enable else 0))
 
@@ -135,10 +146,15 @@ class Plan:
 
     # ---- workspace ----------------------------------------------------------------------------------
     def workspace(self, nbytes):
+        key = (threading.get_ident(), torch.cuda.current_stream(self.device).cuda_stream)
         with self._ws_lock:
-            if self._ws is None or self._ws.numel() < nbytes:
-                self._ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=f"cuda:{self.device}")
-            return self._ws
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < nbytes:
+                if len(self._ws) >= 64:    # threads / streams that came and went: start over rather than grow for ever
+                    self._ws.clear()
+                ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=f"cuda:{self.device}")
+                self._ws[key] = ws
+            return ws
 
     def workspace_for(self, B):
         return self.workspace(self._lib.cacfe_workspace_bytes(self._handle, int(B)))
@@ -152,6 +168,15 @@ class Plan:
         if x.dtype != torch.float32:
             raise TypeError(f"{what}: float32 required, got {x.dtype}")
         return x if x.is_contiguous() else x.contiguous()
+
+    def _check_out(self, out, shape, what):
+        """A caller-supplied result tensor goes to the kernels as a raw pointer: anything but the exact shape, dtype,
+        device and a dense layout would be an out-of-bounds device write, so it is refused here."""
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.device.index == self.device):
+            raise ValueError(f"{what}: out must be a CUDA tensor on cuda:{self.device}")
+        if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != tuple(shape):
+            raise ValueError(f"{what}: out must be contiguous float32 {tuple(shape)}, got {out.dtype} {tuple(out.shape)}")
+        return out
 
     # The C ABI takes 1..65535 batch entries per call (grid.y).  The reference's callables accept any batch, the empty one
     # included (tf.data hands out whatever the last partial batch holds): an empty batch returns an empty result of the right
@@ -182,6 +207,8 @@ class Plan:
         B = raw.shape[0]
         if out is None:
             out = torch.empty(self.feature_shape(B), dtype=torch.float32, device=raw.device)
+        else:
+            self._check_out(out, self.feature_shape(B), "frontend")
         if B == 0:
             return out
         ws = self.workspace_for(min(B, self.MAX_BATCH))
@@ -191,13 +218,27 @@ class Plan:
 
     def frontend_pcen(self, raw, params=None, out=None):
         raw = self._check_in(raw, "frontend_pcen")
+        if raw.dim() != 2 or raw.shape[1] != self.config.n_samples:
+            raise ValueError(f"frontend_pcen: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
         B = raw.shape[0]
+        shape = (B, self.n_frames, self.config.n_mels)
         if out is None:
-            out = torch.empty((B, self.n_frames, self.config.n_mels), dtype=torch.float32, device=raw.device)
+            out = torch.empty(shape, dtype=torch.float32, device=raw.device)
+        else:
+            self._check_out(out, shape, "frontend_pcen")
         if B == 0:
             return out
-        ws = self.workspace_for(B)
         params = params or pcen_params()
+        if B > self.MAX_BATCH:
+            # clips are independent only when the min-max is not tensor-wide (tfpcen.py:105-110 spans the whole call)
+            if params.norm_scope == _lib.NORM_TENSOR:
+                raise ValueError(f"frontend_pcen: a tensor-wide min-max takes at most {self.MAX_BATCH} clips per call")
+            ws = self.workspace_for(self.MAX_BATCH)
+            self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_frontend_pcen(
+                self._handle, ctypes.byref(params), _ptr(raw[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, _ptr(ws),
+                _stream(self.device))))
+            return out
+        ws = self.workspace_for(B)
         _lib.check(self._lib.cacfe_frontend_pcen(self._handle, ctypes.byref(params), _ptr(raw), _ptr(out), B, _ptr(ws),
                                                  _stream(self.device)))
         return out

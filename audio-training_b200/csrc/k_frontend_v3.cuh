@@ -63,6 +63,18 @@ __host__ __device__ inline VSmem v3_smem_layout(int hop, int mel_quads) {
   return s;
 }
 
+#ifdef CACFE_K1_JITTER
+// Race hunting without compute-sanitizer (tests/test_gpu_parity.py::test_k1_jitter): a pseudo-random pause before every
+// hand-over operation.  A schedule-dependent result shows up as a run that differs from the others.
+__device__ __forceinline__ void k1_jitter(unsigned salt) {
+  unsigned h = (unsigned)clock() * 2654435761u + salt * 40503u + threadIdx.x * 97u + blockIdx.x * 1315423911u;
+  h ^= h >> 15;
+  __nanosleep(h & 0x7ffu);   // 0 .. 2 us
+}
+#else
+__device__ __forceinline__ void k1_jitter(unsigned) {}
+#endif
+
 // Mel job tables of the plan (mel_jobs.h), device copies.
 struct MelArgs {
   const float4* tw4;  // [32][64] stage twiddles, packed per output pair: (cos k, cos k+1, sin k, sin k+1)
@@ -178,6 +190,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
     __syncwarp();
+    k1_jitter(5u * (unsigned)i + 2u);
     if (lane == 0) mbar_arrive(smem_u32(&s_norm[s]));
   };
 
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     group_barrier(1 + g, 64);
     if (t64 == 0) {
       const int s = i & 1;
+      k1_jitter(5u * (unsigned)i + 1u);
       __threadfence_block();
       const int old = atomicAdd(&s_done[s], 1);
       if (old == kVGroups - 1) {

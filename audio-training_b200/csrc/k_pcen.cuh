@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
         // the root is monotone: the extremes of p are the roots of the extremes of y (pcen_extremes_kernel takes them with
         // the same instruction sequence APPLY uses) -- two MUFU per element instead of three in the pass they bound
         const float yy = pcen_y(v, m, a);
-        mn = fminf(mn, yy);
-        mx = fmaxf(mx, yy);
+        mn = min_nan(mn, yy);   // NaN-propagating like tf.reduce_min / reduce_max (tfpcen.py:108-109)
+        mx = max_nan(mx, yy);
       } else {
         float p = pcen_point(v, m, a);
-        if (MODE == PCEN_APPLY) p = fmaxf(fminf(fmaf(p - shift, scale, -1.0f), 1.0f), -1.0f);
+        // clamp to [-1, 1] with NaN passing through: a constant tensor (range 0 -> 0 * inf) gives NaN as the reference's 0 / 0 does
+        if (MODE == PCEN_APPLY) p = max_nan(min_nan(fmaf(p - shift, scale, -1.0f), 1.0f), -1.0f);
         y[(size_t)t * a.inner] = p;
       }
     };
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
     for (; t < a.T; ++t) point(ld_stream(x + (size_t)t * a.inner), t);
   }
   if (MODE == PCEN_REDUCE) {
-    block_minmax(mn, mx, scratch);
+    block_minmax_nan(mn, mx, scratch);
     if (threadIdx.x == 0) a.partial[(size_t)clip * gridDim.x + blockIdx.x] = make_float2(mn, mx);
   }
 }
@@ -136,10 +137,10 @@ __global__ void __launch_bounds__(256) pcen_extremes_kernel(const float2* __rest
   const float2* p = partial + (size_t)blockIdx.x * per_entry;
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < per_entry; i += blockDim.x) {
-    mn = fminf(mn, p[i].x);
-    mx = fmaxf(mx, p[i].y);
+    mn = min_nan(mn, p[i].x);
+    mx = max_nan(mx, p[i].y);
   }
-  block_minmax(mn, mx, scratch);
+  block_minmax_nan(mn, mx, scratch);
   if (threadIdx.x == 0) {
     const float pmn = pcen_root(mn, a), pmx = pcen_root(mx, a);
     extremes[blockIdx.x] = raw ? make_float2(pmn, pmx) : make_float2(pmx - pmn, pmn);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) pcen_scan_kernel(const PcenAr
     const int per = (T + 31) / 32;                      // time steps per lane
     const int t_lo = min(lane * per, T), t_hi = min(t_lo + per, T);
     for (int c = 0; c < C; ++c) {
+      const float x0 = s[c];   // initial state, read before any lane writes its results back in place (step 3)
       // 1. this lane's run as an affine map of the incoming state
       float fa = 1.0f, fb = 0.0f;
       for (int t = t_lo; t < t_hi; ++t) {
@@ -247,17 +249,18 @@ __global__ void __launch_bounds__(kScanWarps * 32) pcen_scan_kernel(const PcenAr
         ea = 1.0f;
         eb = 0.0f;
       }
-      float m = fmaf(ea, s[c], eb);
+      float m = fmaf(ea, x0, eb);
+      __syncwarp();   // every lane has read its inputs of steps 1-2 before lane 0 overwrites s[c]
       // 3. the run again, from the right state, with the compression
       for (int t = t_lo; t < t_hi; ++t) {
         const float v = s[t * C + c];
         m = __fadd_rn(__fmul_rn(a.w, v), __fmul_rn(a.one_minus_w, m));
         float p = pcen_point(v, m, a);
         if (MODE == PCEN_REDUCE) {
-          mn = fminf(mn, p);
-          mx = fmaxf(mx, p);
+          mn = min_nan(mn, p);
+          mx = max_nan(mx, p);
         } else {
-          if (MODE == PCEN_APPLY) p = fminf(fmaf(p - shift, scale, -1.0f), 1.0f);
+          if (MODE == PCEN_APPLY) p = max_nan(min_nan(fmaf(p - shift, scale, -1.0f), 1.0f), -1.0f);
           s[t * C + c] = p;
         }
       }
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) pcen_scan_kernel(const PcenAr
     }
   }
   if (MODE == PCEN_REDUCE) {
-    block_minmax(mn, mx, scratch);
+    block_minmax_nan(mn, mx, scratch);
     if (threadIdx.x == 0) a.partial[blockIdx.x] = make_float2(mn, mx);
   }
 }

@@ -177,7 +177,9 @@ def mel_from_spectrogram(spectogram, model_name="", pcen=True):
     plan = rt.get_plan(_config(power=1 if pcen else 2, channels=channels, out_layout="bmtc"), t.device.index, MEL_WEIGHTS)
     out = plan.mel_from_spectrogram(t)
     if not pcen:
-        out = plan.compress(plan.compress(out, "power_to_db"), "minmax")
+        # the reference runs this branch per record inside read_tfrecord (tfdataset.py:1093-1099): the dB reference
+        # maximum and the min-max are per example, so a batch must not share them
+        out = plan.compress(plan.compress(out, "power_to_db", per_clip=True), "minmax", per_clip=True)
     return restore(out[0] if single else out)
 
 
