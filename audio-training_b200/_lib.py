@@ -70,6 +70,7 @@ PROTOTYPES = {
     "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "cacfe_stft_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "cacfe_stft": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cacfe_stft_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "cacfe_pcen_backward_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int]),
     "cacfe_pcen_backward": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
                                     c_int, c_int, c_void_p, c_void_p]),

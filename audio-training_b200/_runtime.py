@@ -243,19 +243,23 @@ class Plan:
                                                  _stream(self.device)))
         return out
 
-    def stft(self, raw):
+    def stft(self, raw, return_stats=False):
         """raw [B, n_samples] -> |X| (power 1) or |X|^2 spectrogram [B, n_fft/2+1, T] in the plan's framing
-        (audiodataset.py:1301-1303: the stored `audio/spectogram` field; the input of mel_from_spectrogram)."""
+        (audiodataset.py:1301-1303: the stored `audio/spectogram` field; the input of mel_from_spectrogram).
+        return_stats=True (plans with normalize=True): also the per-clip (max - min, min) pairs [B, 2] of the
+        normalisation's min/max pass -- range 0 is the reference's silent-window test (audiodataset.py:1311-1323)."""
         raw = self._check_in(raw, "stft")
         if raw.dim() != 2 or raw.shape[1] != self.config.n_samples:
             raise ValueError(f"stft: expected [B, {self.config.n_samples}], got {tuple(raw.shape)}")
         B = raw.shape[0]
         out = torch.empty((B, self.n_bins, self.n_frames), dtype=torch.float32, device=raw.device)
+        stats = torch.empty((B, 2), dtype=torch.float32, device=raw.device) if return_stats else None
         if B == 0:
-            return out
+            return (out, stats) if return_stats else out
         ws = self.workspace(self._lib.cacfe_stft_workspace_bytes(self._handle, B))
-        _lib.check(self._lib.cacfe_stft(self._handle, _ptr(raw), _ptr(out), B, _ptr(ws), _stream(self.device)))
-        return out
+        _lib.check(self._lib.cacfe_stft_stats(self._handle, _ptr(raw), _ptr(out), _ptr(stats), B, _ptr(ws),
+                                              _stream(self.device)))
+        return (out, stats) if return_stats else out
 
     def sosfilt(self, sos, x):
         """scipy.signal.sosfilt(sos, x) along the last axis (float64 recurrence, float32 result) on the device."""

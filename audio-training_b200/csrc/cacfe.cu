@@ -811,9 +811,10 @@ size_t cacfe_stft_workspace_bytes(const cacfe_plan* p, int B) {
   return frontend_ws_bytes(B) + align256((size_t)nb * p->n_bins * p->n_frames * sizeof(float));
 }
 
-int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, void* stream) {
+int cacfe_stft_stats(cacfe_plan* p, const float* raw, float* spec, float* range_min, int B, void* ws, void* stream) {
   if (!p || !raw || !spec || !ws) return fail(CACFE_EINVAL, "stft: null argument");
   if (B < 1) return fail(CACFE_ESHAPE, "stft: B=%d", B);
+  if (range_min && !p->cfg.normalize) return fail(CACFE_EINVAL, "stft_stats: the per-clip statistics exist only when normalize=1");
   CUDA_TRY(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   float* staging = (float*)((char*)ws + frontend_ws_bytes(B));
@@ -822,11 +823,18 @@ int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, vo
     const int nb = B - b0 < kStftChunk ? B - b0 : kStftChunk;
     int rc = launch_frontend(p, raw + (size_t)b0 * p->cfg.n_samples, staging, nb, cacfe::LAYOUT_SPEC, 1, ws, st);
     if (rc != CACFE_OK) return rc;
+    if (range_min)  // the (max - min, min) pairs K0 left in the workspace for this chunk (launch_frontend's layout)
+      CUDA_TRY(cudaMemcpyAsync(range_min + 2 * (size_t)b0, (char*)ws + align256((size_t)nb * kMaxSplits * sizeof(float2)),
+                               (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
     dim3 grid((p->n_bins + cacfe::kTrTile - 1) / cacfe::kTrTile, (p->n_frames + cacfe::kTrTile - 1) / cacfe::kTrTile, nb);
     cacfe::spec_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(staging, spec + (size_t)b0 * per_clip, p->n_frames, p->n_bins);
     if ((rc = check_launch(p, "stft transpose")) != CACFE_OK) return rc;
   }
   return CACFE_OK;
+}
+
+int cacfe_stft(cacfe_plan* p, const float* raw, float* spec, int B, void* ws, void* stream) {
+  return cacfe_stft_stats(p, raw, spec, nullptr, B, ws, stream);
 }
 
 int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, int B, int T, void* stream) {

@@ -158,7 +158,13 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v4_kernel(const Fronten
     // the unscaled power would underflow (range^2 * 1e-7 below the f32 normals) take the exact path as well.
     const int p_lo = a.origin + a.hop * ta;
     const int p_hi = p_lo + a.hop + kFft;
-    const bool fast = p_lo >= 0 && p_hi <= a.n_samples && (a.norm == nullptr || !(sc > 1.0e12f));
+    bool fast = p_lo >= 0 && p_hi <= a.n_samples && (a.norm == nullptr || !(sc > 1.0e12f));
+#ifndef CACFE_V4_SUBTRACT
+    // The subtraction of the clip minimum is itself invisible to bins >= 2 (mn DFT(w) lives in bins 0 and +-1): it only keeps
+    // the f32 products w x from drowning a small signal in a large DC.  Clips whose minimum is within 2x their range of zero load w x
+    // directly (|x| <= 3 range: the rounding of w x stays at the level of the normalised path); the others take the exact path.
+    if (a.norm != nullptr && !(fabsf(mn) * sc <= 4.0f)) fast = false;   // |mn| <= 2 range; NaN -> exact path (all NaN)
+#endif
     float post = fast ? sc : 1.0f;
 
     float re[64], im[64];
@@ -172,14 +178,21 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v4_kernel(const Fronten
         const float4 t1 = s_tw4[t64];
         const float win_c = t1.y, win_s = -t1.w;
         if (fast) {
+#ifdef CACFE_V4_SUBTRACT
           const cacfe_f2 mn2 = cacfe_pk(mn, mn);
+#endif
 #pragma unroll
           for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
             const int n = 64 * q + t64;
             const cacfe_f2 wv = cacfe_pk(fmaf(kWinA[q], win_c, fmaf(kWinB[q], win_s, 0.5f)),
                                          fmaf(kWinA[q + 1], win_c, fmaf(kWinB[q + 1], win_s, 0.5f)));
+#ifdef CACFE_V4_SUBTRACT
             const cacfe_f2 xa = cacfe_mul2(cacfe_sub2(cacfe_pk(fa[n], fa[n + 64]), mn2), wv);
             const cacfe_f2 xb = cacfe_mul2(cacfe_sub2(cacfe_pk(fb[n], fb[n + 64]), mn2), wv);
+#else
+            const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv);
+            const cacfe_f2 xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
+#endif
             re[q] = cacfe_lo(xa);
             re[q + 1] = cacfe_hi(xa);
             im[q] = cacfe_lo(xb);

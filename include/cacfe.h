@@ -152,6 +152,11 @@ int cacfe_frontend(cacfe_plan* plan, const float* raw_dev, float* feat_dev, int 
  * of the plan otherwise.  raw_dev [B][n_samples] -> spec_dev [B][n_fft/2+1][T] (t contiguous, what path C reads). */
 size_t cacfe_stft_workspace_bytes(const cacfe_plan* plan, int B); /* includes a 64-clip [t][k] staging buffer */
 int cacfe_stft(cacfe_plan* plan, const float* raw_dev, float* spec_dev, int B, void* workspace_dev, void* stream);
+/* the same, and (plans with normalize = 1) range_min_dev [B][2] receives each clip's (max - min, min): max - min == 0 is the
+ * reference's silent-window test  a_max == a_min  (audiodataset.py:1311-1323), answered by the pass the normalisation
+ * needs anyway.  range_min_dev may be NULL. */
+int cacfe_stft_stats(cacfe_plan* plan, const float* raw_dev, float* spec_dev, float* range_min_dev, int B,
+                     void* workspace_dev, void* stream);
 
 /* ---- a9: stored spectrogram -> mel.  tfdataset.py:1082-1099.  spec_dev [B][n_fft/2+1][T]. */
 int cacfe_mel_from_spectrogram(cacfe_plan* plan, const float* spec_dev, float* feat_dev, int B, int T, void* stream);

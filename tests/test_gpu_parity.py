@@ -485,6 +485,67 @@ def test_stored_spectrogram_producer(oracle, clips, xn, bank):
     assert np.all(np.abs(short[0] - want) <= 1e-4 * want + 2e-6 * want.max(axis=0, keepdims=True))
 
 
+def test_load_data_against_reference_golden(oracle):
+    """audiodataset.load_data (audiodataset.py:1171-1331) end to end on the device: the same windows, exceptions and
+    raw_length as the reference's own function executed over the stand-ins (tests/golden/load_data.*), its stored
+    spectrogram within the FP32-FFT tolerance of the one the reference code produced and of the f64 oracle, the silent
+    window rejected from the normalisation's own min/max pass, and the bulk form agreeing with the single calls."""
+    import json
+    from audio_training_b200 import audiodataset as ad
+    with open(os.path.join(GOLDEN, "load_data.json")) as fh:
+        meta = json.load(fh)
+    arrays = np.load(os.path.join(GOLDEN, "load_data.npz"))
+    sr = meta["sr"]
+    frames = oracle.synth_recording(meta["seconds"], sr=sr, seed=meta["seed"])
+    silent = frames.copy()
+    s0, s1, level = meta["silence"]
+    silent[int(s0 * sr):int(s1 * sr)] = level
+
+    class Config:
+        segment_length, segment_stride, hop_length, fmin, fmax, n_mels, htk, break_freq = 3, 1, 281, 50, 11000, 160, True, 1000
+
+    def scripted(fracs):
+        fr = list(fracs)
+        return lambda lo, hi: int(lo + np.floor((fr.pop(0) if fr else 0.0) * (hi - lo)))
+
+    kept = []
+    for idx, case in enumerate(meta["cases"]):
+        src = silent if case["silent"] else frames
+        args = (Config(), case["start_s"], src, sr)
+        kw = dict(end=case["end"], use_padding=case["use_padding"], randint=scripted(case["fracs"]))
+        if case["error"] is not None:
+            with pytest.raises(Exception, match=case["error"]):
+                ad.load_data(*args, **kw)
+            continue
+        spec = ad.load_data(*args, **kw)
+        assert isinstance(spec, ad.SpectrogramData) and spec.buttered is None and spec.short_features is None
+        assert zlib.crc32(np.float32(spec.raw).tobytes()) == case["raw_crc"] and spec.raw_length == case["raw_length"]
+        assert list(spec.spectogram.shape) == case["spec_shape"] and spec.spectogram.dtype == np.float32
+        want = arrays[f"spec_{idx}"]
+        sub = spec.spectogram[::meta["sub"][0], ::meta["sub"][1]]
+        colmax = spec.spectogram.max(axis=0)[::meta["sub"][1]][None, :]
+        assert np.all(np.abs(sub - want) <= 1e-4 * want + 2e-6 * colmax), idx
+        truth = np.abs(oracle.stft_librosa(oracle.normalize(spec.raw, np.float32)))
+        assert np.all(np.abs(spec.spectogram - truth) <= 1e-4 * truth + 2e-6 * truth.max(axis=0, keepdims=True)), idx
+        kept.append((case, spec))
+    # bulk form: one upload, one launch sequence; per-window results or the exception the reference would raise
+    cases = [c for c in meta["cases"] if not c["silent"] and not c["use_padding"]]
+    fr = [f for c in cases for f in (c["fracs"] + [0.0] * len(c["draws"]))[:len(c["draws"])]]   # one fraction per draw made
+    res = ad.load_data_batch(Config(), [c["start_s"] for c in cases], frames, sr, ends=[c["end"] for c in cases],
+                             randint=scripted(fr))
+    singles = {id(c): s for c, s in kept}
+    for c, r in zip(cases, res):
+        if c["error"] is not None:
+            assert isinstance(r, ad.OutOfBounds)
+        else:
+            assert np.array_equal(r.raw, singles[id(c)].raw) and np.array_equal(r.spectogram, singles[id(c)].spectogram)
+    mixed = ad.load_data_batch(Config(), [2.0, 6.5, 12.0], silent, sr)
+    assert isinstance(mixed[1], ad.MaxIsMin) and isinstance(mixed[0], ad.SpectrogramData) and isinstance(mixed[2], ad.SpectrogramData)
+    fields = ad.record_fields(mixed[0])
+    mel = td.mel_from_spectrogram(fields["audio/spectogram"].reshape(2049, -1))     # tfdataset.py:1083: the reader's reshape
+    assert mel.shape == (160, fields["audio/spectogram"].size // 2049, 1) and np.isfinite(mel).all()
+
+
 # ------------------------------------------------------------------------------------------------ a15 variants
 def test_multi_resolution_variants(oracle, golden_banks, xn):
     """raw_to_mel_rgb / raw_to_mel_dual (tfdataset.py:1818-2004): 1024- and 2048-point STFTs through the 4096-point kernel

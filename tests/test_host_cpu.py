@@ -73,6 +73,69 @@ def test_window_table_matches_reference(oracle):
         assert calls == [h for (h, _) in case["offsets"]]
 
 
+def _load_data_cases():
+    with open(os.path.join(GOLDEN, "load_data.json")) as fh:
+        meta = json.load(fh)
+    return meta, np.load(os.path.join(GOLDEN, "load_data.npz"))
+
+
+def _scripted_randint(fracs, log):
+    fr = list(fracs)
+
+    def randint(lo, hi):
+        frac = fr.pop(0) if fr else 0.0
+        v = int(lo + np.floor(frac * (hi - lo)))
+        log.append([int(lo), int(hi), v])
+        return v
+    return randint
+
+
+def test_load_data_window_selection_matches_reference(oracle):
+    """audiodataset.load_data's scalar part (select_window / cut_window) against the reference's own function executed over
+    the stand-ins (oracle/ref_shim/gen_load_data_golden.py): same `raw` bytes, same raw_length, the same random draws asked
+    for in the same order, the same exceptions; and the oracle's restatement of the stored spectrogram against the one the
+    reference code produced."""
+    import zlib
+    from audio_training_b200 import audiodataset as ad
+    meta, arrays = _load_data_cases()
+    sr = meta["sr"]
+    frames = oracle.synth_recording(meta["seconds"], sr=sr, seed=meta["seed"])
+    assert float(np.sum(frames, dtype=np.float64)) == meta["frames_checksum"], "synthetic recording drifted"
+    silent = frames.copy()
+    s0, s1, level = meta["silence"]
+    silent[int(s0 * sr):int(s1 * sr)] = level
+    for idx, case in enumerate(meta["cases"]):
+        src = silent if case["silent"] else frames
+        log = []
+        randint = _scripted_randint(case["fracs"], log)
+        try:
+            lo, hi, pl, pr, raw_length = ad.select_window(3, case["start_s"], len(src), sr, case["end"], case["use_padding"], randint)
+        except ad.OutOfBounds as exc:
+            assert case["error"] == str(exc) == "Out of frame bounds", (idx, case)
+            assert log == case["draws"]
+            continue
+        raw = ad.cut_window(src, lo, hi, pl, pr)
+        assert log == case["draws"], (idx, log, case["draws"])
+        if case["error"] == "Max is min":
+            assert raw.max() == raw.min()
+            continue
+        assert case["error"] is None
+        assert raw.dtype == np.float32 and raw.shape[0] == case["raw_len"] == 3 * sr
+        assert zlib.crc32(raw.tobytes()) == case["raw_crc"], idx
+        assert raw_length == case["raw_length"]
+        nz = np.nonzero(raw)[0]
+        assert (int(nz[0]), int(nz[-1])) == (case["first_nonzero"], case["last_nonzero"])
+        # the oracle's restatement of  np.abs(librosa.stft(normalize_data(raw)))  vs what the reference code stored
+        want = arrays[f"spec_{idx}"]
+        got = np.abs(oracle.stft_librosa(oracle.normalize(raw, np.float32), 4096, 281, "constant", np.float32))
+        assert list(got.shape) == case["spec_shape"]
+        sub = got[::meta["sub"][0], ::meta["sub"][1]]
+        assert np.allclose(sub, want, rtol=1e-5, atol=1e-5 * float(want.max()))
+    fields = ad.record_fields(ad.SpectrogramData(raw, got, raw_length, None, None, None))
+    assert fields["audio/raw"].dtype == np.float32 and fields["audio/raw"].shape == (3 * sr,)
+    assert fields["audio/spectogram"].dtype == np.float32 and fields["audio/spectogram"].shape == (got.size,)
+
+
 def test_layers_keep_reference_weights(golden):
     layer = atb.PCEN()
     sd = layer.state_dict()
