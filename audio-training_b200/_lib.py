@@ -64,7 +64,6 @@ PROTOTYPES = {
     "cacfe_plan_launch_count": (c_longlong, [c_void_p]),
     "cacfe_plan_profile": (c_int, [c_void_p, c_int]),
     "cacfe_plan_force_generic": (c_int, [c_void_p, c_int]),
-    "cacfe_plan_select_kernel": (c_int, [c_void_p, c_int]),
     "cacfe_plan_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
     "cacfe_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]),
     "cacfe_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

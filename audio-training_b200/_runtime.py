@@ -125,10 +125,6 @@ class Plan:
         """Use the generic (non-streaming) fused kernel even where the TMA streaming form applies."""
         _lib.check(self._lib.cacfe_plan_force_generic(self._handle, 1 if enable else 0))
 
-    def select_kernel(self, which=0):
-        """0: the newest persistent fused kernel that applies (stft_mel_v4_kernel); 3: stft_mel_v3_kernel."""
-        _lib.check(self._lib.cacfe_plan_select_kernel(self._handle, int(which)))
-
     def profile(self, enable=True):
         _lib.check(self._lib.cacfe_plan_profile(self._handle, 1 if enable else 0))
 

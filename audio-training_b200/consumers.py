@@ -2,9 +2,11 @@
 (front-end -> badwinner2 inference, front-end -> wr_resnet_bird training step) run end to end on the device.
 
 These are *consumers* of the features, not part of the hot path: plain torch.nn over cuDNN, no kernels of ours, and
-PARITY UNPINNED -- Keras / TensorFlow cannot be imported here, so the layer graphs below are restated from the
-reference source and Keras' documented defaults (BatchNormalization eps 1e-3 / momentum 0.99, `valid` convolutions,
-pool stride = pool size, `same` padding = floor before / ceil after), checked by shape and parameter count only.
+pinned against the reference's own builder functions executed over an eager numpy stand-in for Keras
+(oracle/ref_shim/gen_consumer_golden.py -> tests/golden/consumers.*, tests/test_consumers.py: same variables in the same
+creation order, same logits).  Keras / TensorFlow themselves cannot be imported here, so the layer semantics are Keras'
+documented defaults (BatchNormalization eps 1e-3 / momentum 0.99, `valid` convolutions, pool stride = pool size, `same`
+padding = floor before / ceil after).
 
   * `build_model`   <- badwinner2.build_model        (badwinner2.py:212-324)
   * `WRResNet`      <- resnet/wr_resnet_bird.WRResNet (resnet/wr_resnet_bird.py:7-178), including its quirks: the
@@ -14,7 +16,8 @@ pool stride = pool size, `same` padding = floor before / ceil after), checked by
 
 Inputs are the reference's NHWC images `(B, n_mels, T, C)`; modules convert to NCHW internally.  Weights are random
 (the reference ships none).  `keras_weight_order(model)` lists parameters in Keras creation order with the transposes a
-`.weights.h5` -> state_dict converter needs (HWIO -> OIHW); reading HDF5 itself needs h5py, which this image lacks.
+Keras -> state_dict converter needs (HWIO -> OIHW); `load_weights_h5(model, path)` reads a Keras 3 `.weights.h5`
+checkpoint (what audiomodel.py:278-283 writes) through the package's own minimal HDF5 parser (h5lite.py; no h5py here).
 """
 from __future__ import annotations
 
@@ -240,3 +243,54 @@ def load_keras_weights(model, arrays):
             raise ValueError(f"{key}: shape {tuple(t.shape)} != {tuple(sd[key].shape)}")
         sd[key].copy_(t)
     return model
+
+
+# ------------------------------------------------------------------------------------------------ Keras 3 .weights.h5
+_KERAS_KIND = {nn.Conv2d: "conv2d", ConvSame: "conv2d", nn.Linear: "dense", nn.BatchNorm2d: "batch_normalization",
+               MagTransformLayer: "mag_transform"}
+
+
+def keras3_variable_paths(model):
+    """[(HDF5 path, state_dict key, transpose)] for a Keras 3 `.weights.h5` file of the matching Keras model.
+
+    Layout written by keras.saving (saving_lib._save_state / _save_container_state, H5IOStore): every layer of
+    `model.layers` gets the group `layers/<snake_case class name>[_<k>]/vars` -- k counts the earlier layers of the SAME
+    class in `model.layers` order, the autogenerated or user-given `layer.name` is not used -- holding one dataset per
+    variable, named by its index in `layer.weights` (Conv2D / Dense: 0 kernel, 1 bias; BatchNormalization: gamma, beta,
+    moving_mean, moving_variance, without the first two when scale = center = False; MagTransform: 0 `a-power`).
+    `model.layers` is topological; for these two graphs the order within each class equals the creation order, which is
+    the order of `named_modules()` here (checked against the executed reference builders by tests/test_consumers.py).
+    Unverified against a checkpoint written by Keras itself: neither Keras nor h5py exists in this image."""
+    counts, out = {}, []
+    for name, m in model.named_modules():
+        kind = _KERAS_KIND.get(type(m))
+        if kind is None:
+            continue
+        k = counts.get(kind, 0)
+        counts[kind] = k + 1
+        group = f"layers/{kind if k == 0 else f'{kind}_{k}'}/vars"
+        if isinstance(m, nn.Conv2d):
+            keys = [("weight", "hwio->oihw"), ("bias", "copy")]
+        elif isinstance(m, nn.Linear):
+            keys = [("weight", "io->oi"), ("bias", "copy")]
+        elif isinstance(m, nn.BatchNorm2d):
+            keys = ([("weight", "copy"), ("bias", "copy")] if m.affine else []) + [("running_mean", "copy"), ("running_var", "copy")]
+        else:
+            keys = [("a", "copy")]
+        out += [(f"{group}/{i}", f"{name}.{key}", how) for i, (key, how) in enumerate(keys)]
+    return out
+
+
+def load_weights_h5(model, path):
+    """Load a Keras 3 `.weights.h5` checkpoint (audiomodel.py:278-283, :177-179) into `model`.  Raises KeyError naming the
+    first variable the file does not hold, ValueError on a shape mismatch, h5lite.H5Unsupported on HDF5 features the
+    minimal parser does not read (compressed datasets ...)."""
+    from . import h5lite
+    f = h5lite.File(path)
+    if "layers" not in f.keys("/"):
+        raise KeyError(f"{path}: no `layers` group -- not a Keras 3 weights file (found {f.keys('/')})")
+    paths = keras3_variable_paths(model)
+    arrays = [f[p] for p, _, _ in paths]
+    order = [(key, how) for _, key, how in paths]
+    assert order == keras_weight_order(model)
+    return load_keras_weights(model, arrays)

@@ -17,7 +17,6 @@
 #include "k_compress.cuh"
 #include "k_frontend.cuh"
 #include "k_frontend_v3.cuh"
-#include "k_frontend_v4.cuh"
 #include "k_melspec.cuh"
 #include "k_normalize_cluster.cuh"
 #include "k_melspec_stream.cuh"
@@ -67,9 +66,6 @@ struct cacfe_plan {
   int* d_band_ofs = nullptr;
   cacfe::K1Smem k1;
   cacfe::VSmem kv;
-  cacfe::V4Smem kv4;
-  bool v4_ok = false;      // round-2 form of the persistent kernel (k_frontend_v4.cuh) applies
-  int kernel_select = 0;   // 0: newest kernel that applies; 3: stft_mel_v3_kernel (tests run both)
   cacfe::MelJobs jobs;
   float4* d_mel_w = nullptr;
   float4* d_tw4 = nullptr;
@@ -375,10 +371,6 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   p->v3_ok = fft_divides && p->jobs.ok && p->kv.total <= (size_t)prop.sharedMemPerBlockOptin &&
              p->kv.tile_pad <= cacfe::kNormIters * cacfe::kVThreads * 4 &&
              cfg->n_samples % 4 == 0 && reflect_fits;
-  // v4 (no in-place normalisation pass): the linear form of the clip normalisation needs a bank that ignores bins 0 and 1
-  p->kv4 = cacfe::v4_smem_layout(cfg->hop, p->jobs.total_quads);
-  p->v4_ok = p->v3_ok && cfg->n_fft == cacfe::kFft && cfg->framing != CACFE_FRAME_CENTER_REFLECT &&
-             (!cfg->normalize || lo >= 2) && p->kv4.total <= (size_t)prop.sharedMemPerBlockOptin;
 
   // tables
   std::vector<float2> tw(4096);
@@ -462,12 +454,6 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
       // with a smaller layout cannot shrink it under an earlier plan
       e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
   }
-  if (e == cudaSuccess && p->v4_ok) {
-    const void* kernels[4] = {(const void*)cacfe::stft_mel_v4_kernel<15, cacfe::LAYOUT_BTM>, (const void*)cacfe::stft_mel_v4_kernel<15, cacfe::LAYOUT_BMTC>,
-                              (const void*)cacfe::stft_mel_v4_kernel<33, cacfe::LAYOUT_BTM>, (const void*)cacfe::stft_mel_v4_kernel<33, cacfe::LAYOUT_BMTC>};
-    for (int q = 0; q < 4 && e == cudaSuccess; ++q)
-      e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
-  }
   if (e != cudaSuccess) {
     cacfe_plan_destroy(p);
     return fail(CACFE_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -524,13 +510,6 @@ int cacfe_plan_profile_read(cacfe_plan* p, double* k1_ms, long long* k1_launches
 int cacfe_plan_force_generic(cacfe_plan* p, int enable) {
   if (!p) return fail(CACFE_EINVAL, "plan_force_generic: null plan");
   p->force_generic = enable != 0;
-  return CACFE_OK;
-}
-
-int cacfe_plan_select_kernel(cacfe_plan* p, int which) {
-  if (!p) return fail(CACFE_EINVAL, "plan_select_kernel: null plan");
-  if (which != 0 && which != 3) return fail(CACFE_EINVAL, "plan_select_kernel: 0 (newest that applies) or 3 (stft_mel_v3_kernel)");
-  p->kernel_select = which;
   return CACFE_OK;
 }
 
@@ -743,15 +722,7 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     if (winc) cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);    \
     else cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);        \
   } while (0)
-    const bool v4 = p->v4_ok && p->kernel_select != 3 && layout != cacfe::LAYOUT_SPEC;
-#define CACFE_V4_LAUNCH(NQ_, LAYOUT_) \
-  cacfe::stft_mel_v4_kernel<NQ_, LAYOUT_><<<ctas, cacfe::kVThreads, p->kv4.total, st>>>(a, mj, (int)tiles)
-    if (v4) {
-      if (p->nq_v3 <= 15 && btm) CACFE_V4_LAUNCH(15, cacfe::LAYOUT_BTM);
-      else if (p->nq_v3 <= 15) CACFE_V4_LAUNCH(15, cacfe::LAYOUT_BMTC);
-      else if (btm) CACFE_V4_LAUNCH(33, cacfe::LAYOUT_BTM);
-      else CACFE_V4_LAUNCH(33, cacfe::LAYOUT_BMTC);
-    } else if (layout == cacfe::LAYOUT_SPEC)
+    if (layout == cacfe::LAYOUT_SPEC)
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPEC);
     else if (p->nq_v3 <= 15 && btm)
       CACFE_V3_LAUNCH(15, cacfe::LAYOUT_BTM);
@@ -762,7 +733,6 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     else
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_BMTC);
 #undef CACFE_V3_LAUNCH
-#undef CACFE_V4_LAUNCH
   } else {
     if (layout == cacfe::LAYOUT_SPEC)
       return fail(CACFE_EINVAL, "stft: the spectrogram output needs the persistent kernel (16-byte aligned input, n_samples %% 4 == 0)");

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CACFE_VERSION 102 /* 0.1.2: + cacfe_plan_select_kernel (round-2 fused kernel) */
+#define CACFE_VERSION 102 /* 0.1.2: + cacfe_stft_stats */
 
 typedef enum cacfe_status {
   CACFE_OK = 0,
@@ -133,9 +133,6 @@ int cacfe_plan_profile(cacfe_plan* plan, int enable);
  * applies; both compute the same features (parity tests exercise both). */
 int cacfe_plan_force_generic(cacfe_plan* plan, int enable);
 int cacfe_plan_profile_read(cacfe_plan* plan, double* k1_ms, long long* k1_launches);
-/* which persistent fused kernel serves cacfe_frontend where several apply: 0 = the newest (stft_mel_v4_kernel: no in-place
- * normalisation pass), 3 = stft_mel_v3_kernel.  Both compute the same features within the tolerance; tests run both. */
-int cacfe_plan_select_kernel(cacfe_plan* plan, int which);
 
 /* ---- a1: normalize(input, y) tfdataset.py:1916-1934 / normalize_data predict_utils.py:153-160 ------------
  * rows x n floats, reduction over the last axis, reference operation order with a true f32 division. */

@@ -195,11 +195,10 @@ def test_streaming_and_generic_kernels_agree(oracle, clips, xn, bank):
 
 
 @pytest.mark.parametrize("framing", ["tf_pad_end", "center_zero", "no_pad"])
-def test_v4_and_v3_kernels_agree(oracle, clips, bank, framing):
-    """stft_mel_v4_kernel (round 2: no in-place normalisation pass; the affine clip normalisation is applied to the mel sums
-    of full frames and per sample to the frames that reach into the padding) against stft_mel_v3_kernel and the f64 oracle,
-    with and without the fused normalisation, power 1 and 2, both layouts.  Clip 2 has a DC 300x its range, clip 3 a range
-    of 1e-13 (the degenerate-range branch), clip 4 is constant (NaN, Q1)."""
+def test_fused_kernel_edge_clips(oracle, clips, bank, framing):
+    """The persistent fused kernel on clips that stress the normalisation: clip 2 has a DC 300x its range, clip 3 a range of
+    1e-13, clip 4 is constant (NaN, Q1); with and without the fused normalisation, power 1 and 2, both layouts, against the
+    f64 oracle."""
     x = np.concatenate([clips, oracle.synth_clips(np.arange(90, 93))])
     x[2] = x[2] * 0.01 + 3.0
     x[3] = (x[3] * 1e-13).astype(np.float32)
@@ -210,35 +209,28 @@ def test_v4_and_v3_kernels_agree(oracle, clips, bank, framing):
         for power in (2, 1):
             for layout, ch in (("btm", 1), ("bmtc", 3)):
                 cfg = rt.FrontendConfig(normalize=norm, channels=ch, out_layout=layout, framing=framing, power=power)
-                plan = rt.Plan(cfg, 0, bank)
-                a = plan.frontend(t)
-                plan.select_kernel(3)
-                b = plan.frontend(t)
-                plan.select_kernel(0)
+                a = rt.Plan(cfg, 0, bank).frontend(t)
                 src = xn if norm else x[:4]
+                n_ok = 4 if norm else 3                       # the 1e-13 clip is only meaningful once normalised
                 if framing == "center_zero":
-                    want = np.stack([oracle.get_spect(c, power=power, pad_mode="constant")[..., 0] for c in src[:3]])
+                    want = np.stack([oracle.get_spect(c, power=power, pad_mode="constant")[..., 0] for c in src[:n_ok]])
                 else:
-                    want = oracle.raw_to_mel(src[:3], bank, 4096, 281, framing == "tf_pad_end", 0, power)
+                    want = oracle.raw_to_mel(src[:n_ok], bank, 4096, 281, framing == "tf_pad_end", 0, power)
                 ga = (a.transpose(1, 2) if layout == "btm" else a[..., ch - 1]).cpu().numpy()
-                gb = (b.transpose(1, 2) if layout == "btm" else b[..., ch - 1]).cpu().numpy()
                 what = f"{framing} norm {norm} power {power} {layout}"
-                check(oracle, ga[:3], want, what="v4 " + what)
-                check(oracle, gb[:3], want, what="v3 " + what)
+                check(oracle, ga[:n_ok], want, what=what)
                 if norm:
-                    assert np.isnan(ga[4]).all() and np.isnan(gb[4]).all(), what      # constant clip
-                    # range 1e-13: 2 / range overflows nothing, but the unscaled power would underflow: exact path
-                    ok, worst = oracle.within_tolerance(ga[3], gb[3], 2e-4, 2e-5)
-                    assert ok and np.isfinite(ga[3]).all(), (what, worst)
+                    assert np.isnan(ga[4]).all(), what                                # constant clip
                 else:
                     assert np.isfinite(ga).all()
 
 
 def test_k1_jitter():
-    """Stand-in for racecheck (compute-sanitizer does not start on this pool): libcacfe_jitter.so is the same library built
-    with -DCACFE_K1_JITTER, which puts a pseudo-random pause of 0..2 us before every hand-over operation of the persistent
-    fused kernels (tile release / re-arm, barrier waits).  The B = 4096 launch runs 50 times under it (v4), and 10 times
-    through v3 (reflect framing); every run must reproduce the first bit for bit, and the first must equal the plain build."""
+    """Stand-in for racecheck (compute-sanitizer is closed on this pool): libcacfe_jitter.so is the same library built with
+    -DCACFE_K1_JITTER, which puts a pseudo-random pause of 0..2 us before every hand-over operation of the persistent fused
+    kernel (tile release / re-arm by the last group, the warps' arrival on the tile-normalised barrier).  The B = 4096 launch
+    runs 50 times under it, a reflect-framed batch (the extra mbarrier round of the mirror copy) 10 times; every run must
+    reproduce the first bit for bit, and the first must equal the plain build's result."""
     import json
     import subprocess
     import sys
@@ -254,8 +246,8 @@ B = 4096
 g = torch.Generator(device="cuda").manual_seed(3)
 x = torch.rand((B, 144000), generator=g, device="cuda") - 0.5
 res = {}
-for name, cfg, reps, nb in (("v4", rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), int(sys.argv[2]), B),
-                            ("v3", rt.FrontendConfig(normalize=True, channels=1, out_layout="btm", framing="center_reflect"), int(sys.argv[3]), 1024)):
+for name, cfg, reps, nb in (("pad_end", rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), int(sys.argv[2]), B),
+                            ("reflect", rt.FrontendConfig(normalize=True, channels=1, out_layout="btm", framing="center_reflect"), int(sys.argv[3]), 1024)):
     plan = rt.Plan(cfg, 0)
     first = plan.frontend(x[:nb]).clone()
     same = 0
@@ -272,7 +264,7 @@ print(json.dumps(res))
         assert r.returncode == 0, r.stderr[-2000:]
         out[lib] = json.loads(r.stdout.strip().splitlines()[-1])
     jit, plain = out[_lib.JITTER_LIB_PATH], out[_lib.LIB_PATH]
-    for k in ("v4", "v3"):
+    for k in ("pad_end", "reflect"):
         assert jit[k]["finite"] and jit[k]["identical"] == jit[k]["runs"], (k, jit[k])
         assert jit[k]["crc"] == plain[k]["crc"], (k, jit[k], plain[k])
 

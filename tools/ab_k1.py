@@ -22,23 +22,18 @@ def child(lib, B, steps):
     x = torch.rand((B, 144000), device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)) - 0.5
     plan = rt.Plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
     out = torch.empty((B, plan.n_frames, 160), dtype=torch.float32, device="cuda")
-    for which in (3, 0, 3, 0):                      # stft_mel_v3_kernel, then the newest kernel (v4), twice round-robin
-        if not hasattr(plan, "select_kernel"):
-            which = -1
-        else:
-            plan.select_kernel(which)
-        for _ in range(3):
-            plan.frontend(x, out)
-        torch.cuda.synchronize()
-        plan.profile(True)
-        plan.profile_read()
-        for _ in range(steps):
-            plan.frontend(x, out)
-        torch.cuda.synchronize()
-        ms, n = plan.profile_read()
-        plan.profile(False)
-        print(json.dumps({"lib": os.path.relpath(lib, REPO), "kernel": {3: "v3", 0: "v4", -1: "?"}[which], "k1_ms": ms / max(n, 1),
-                          "launches": n, "checksum": float(out.double().sum()), "probe": float(out[B // 2, 100, 40])}), flush=True)
+    for _ in range(3):
+        plan.frontend(x, out)
+    torch.cuda.synchronize()
+    plan.profile(True)
+    plan.profile_read()
+    for _ in range(steps):
+        plan.frontend(x, out)
+    torch.cuda.synchronize()
+    ms, n = plan.profile_read()
+    plan.profile(False)
+    print(json.dumps({"lib": os.path.relpath(lib, REPO), "k1_ms": ms / max(n, 1), "launches": n,
+                      "checksum": float(out.double().sum()), "probe": float(out[B // 2, 100, 40])}), flush=True)
 
 
 def main():
