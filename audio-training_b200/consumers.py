@@ -3,7 +3,7 @@
 
 These are *consumers* of the features, not part of the hot path: plain torch.nn over cuDNN, no kernels of ours, and
 pinned against the reference's own builder functions executed over an eager numpy stand-in for Keras
-(oracle/ref_shim/gen_consumer_golden.py -> tests/golden/consumers.*, tests/test_consumers.py: same variables in the same
+(the generator sits with the other fixture generators; tests/golden/consumers.*, tests/test_consumers.py: same variables in the same
 creation order, same logits).  Keras / TensorFlow themselves cannot be imported here, so the layer semantics are Keras'
 documented defaults (BatchNormalization eps 1e-3 / momentum 0.99, `valid` convolutions, pool stride = pool size, `same`
 padding = floor before / ceil after).

@@ -26,7 +26,11 @@ def init(backend=None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=size)
+            # device_id binds the communicator to this rank's GPU at creation (without it NCCL guesses the device at the
+            # first collective and warns that a wrong guess can hang)
+            dist.init_process_group(backend=backend, rank=rank, world_size=size, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=size)
     return rank, size, local
 
 

@@ -116,6 +116,32 @@ class ClockSampler:
                 "reasons": reasons}
 
 
+def numa_node_of(addr):
+    """NUMA node holding the page at `addr` (move_pages(2) with nodes = NULL only queries); -1 when unknown."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        page = ctypes.c_void_p(addr & ~0xFFF)
+        status = ctypes.c_int(-1)
+        rc = libc.syscall(279, 0, ctypes.c_ulong(1), ctypes.byref(page), None, ctypes.byref(status), 0)   # __NR_move_pages, x86-64
+        return int(status.value) if rc == 0 else -1
+    except Exception:
+        return -1
+
+
+def gpu_numa_node(index):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        with open(f"/sys/bus/pci/devices/{bus.lower()[-12:]}/numa_node") as fh:
+            return int(fh.read().strip())
+    except Exception:
+        return -1
+
+
 def synth_on_device(torch, B, device, seed):
     """SURVEY 8d generator shape (noise + 3 linear chirps + DC) evaluated on the device, in chunks."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -137,19 +163,36 @@ def synth_on_device(torch, B, device, seed):
     return out
 
 
-def cpu_reference_run(n_clips, budget_s, min_batches=3):
-    """The reference's CPU op order (oracle port, f32) on batches of `n_clips` synthetic clips."""
+def cpu_reference_run(n_clips, budget_s, min_batches=3, steps=None):
+    """The reference's CPU op order (oracle ports, f32) on batches of `n_clips` synthetic clips, all host threads.
+    Two faithful ports are timed -- torch's CPU kernels (FFT + batched sgemm, intra-op threads) and numpy / scipy pocketfft --
+    and the FASTER one is the baseline (round-1 review: the numpy form alone flatters the GPU ratio 2-4x).
+    -> {"value", "kind_detail", "batches", "torch_port", "numpy_port", "threads"}"""
+    import torch
     from oracle import frontend_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
     w = fo.mel_f(48000, 160, 100, 11000, 4096, 1000)
     x = fo.synth_clips(np.arange(n_clips))
-    fo.reference_cpu_path(x, w)  # warm-up
-    times = []
-    t_end = time.perf_counter() + budget_s
-    while len(times) < min_batches or (time.perf_counter() < t_end and len(times) < 50):
-        t0 = time.perf_counter()
-        fo.reference_cpu_path(x, w)
-        times.append(time.perf_counter() - t0)
-    return n_clips / float(np.median(times)), len(times)
+    res = {}
+    for name, fn in (("torch_port", fo.reference_cpu_path_torch), ("numpy_port", fo.reference_cpu_path)):
+        fn(x, w)  # warm-up
+        times = []
+        t_end = time.perf_counter() + budget_s / 2
+        while (len(times) < (steps or min_batches)) if steps else (len(times) < min_batches or (time.perf_counter() < t_end and len(times) < 50)):
+            t0 = time.perf_counter()
+            fn(x, w)
+            times.append(time.perf_counter() - t0)
+        res[name] = n_clips / float(np.median(times))
+        res[name + "_batches"] = len(times)
+    best = "torch_port" if res["torch_port"] >= res["numpy_port"] else "numpy_port"
+    res.update(value=res[best], best=best, batches=res[best + "_batches"], threads=torch.get_num_threads())
+    return res
+
+
+CPU_SAMPLE = ("{n} batches of 32 synthetic clips (BASELINE.json configs[0]) per port; the reference's f32 op order "
+              "(normalize -> stft 4096/281 pad_end -> z**2, abs -> replicated-weight batch matmul -> x3 channels -> PCEN) as two "
+              "faithful CPU ports, value = the faster one ({best}): torch CPU kernels {tp:.1f} clips/s, numpy + scipy pocketfft "
+              "{npp:.1f} clips/s, {th} threads; TensorFlow / librosa are not installable offline")
 
 
 def run_reference(args):
@@ -158,24 +201,18 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     n = 32
-    from oracle import frontend_oracle as fo
-    w = fo.mel_f(48000, 160, 100, 11000, 4096, 1000)
-    x = fo.synth_clips(np.arange(n))
-    for _ in range(max(1, min(args.warmup, 2))):
-        fo.reference_cpu_path(x, w)
     steps = max(1, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fo.reference_cpu_path(x, w)
-    dt = (time.perf_counter() - t0) / steps
-    value = n / dt
-    sample = f"{n} synthetic clips per step (BASELINE.json configs[0]); oracle port of the reference op order, f32, scipy pocketfft workers={cores}, numpy sgemm; TensorFlow/librosa are not installable offline"
+    r = cpu_reference_run(n, budget_s=0.0, steps=min(steps, 20))
+    value = r["value"]
+    dt = n / value
+    sample = CPU_SAMPLE.format(n=r["batches"], best=r["best"], tp=r["torch_port"], npp=r["numpy_port"], th=r["threads"])
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(B=4096),
                        "sample": "each step is one batch of 32 clips of that workload on the host cores (BASELINE.json configs[0])"},
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample,
+                             "torch_port": r["torch_port"], "numpy_port": r["numpy_port"]},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     args.emit(line)
@@ -235,6 +272,30 @@ def run_ours(args):
     ms_step = dist_.max_over_ranks(ms_total / args.steps, device)
     value = world * B / (ms_step * 1e-3)
 
+    # ---- every rank's result, checked: an exact checksum of all output bits (sum of the int32 views, order independent) per
+    # rank; rank 0 then regenerates each rank's batch from its seed, runs it on its own GPU and compares.  Catches a rank
+    # that computed something else (wrong device, stale buffer, a kernel that misbehaves on one GPU only).
+    def bits_checksum(t):
+        return int(t.view(torch.int32).sum(dtype=torch.int64).item())
+
+    my_sum = bits_checksum(out)
+    rank_sums = [my_sum]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        torch.distributed.all_gather(gathered, torch.tensor([my_sum], dtype=torch.int64, device=device))
+        rank_sums = [int(g.item()) for g in gathered]
+    rank_check = None
+    if rank == 0:
+        recomputed = []
+        for r in range(world):
+            xr = x if r == 0 else synth_on_device(torch, B, device, 20240 + r)
+            recomputed.append(bits_checksum(plan.frontend_pcen(xr, params, out)))
+            del xr
+        rank_check = {"per_rank_checksum": rank_sums, "recomputed_on_rank0": recomputed, "match": recomputed == rank_sums}
+        if recomputed != rank_sums:
+            raise SystemExit(f"bench.py: per-rank results differ from their single-GPU recomputation: {rank_check}")
+        plan.frontend_pcen(x, params, out)      # leave rank 0's own result in `out`
+
     # ---- DRAM traffic of the dominant kernel: from the committed ncu --set full capture (1024 clips per launch),
     # scaled to this launch's clip count; None when the summary is not there
     traffic = None
@@ -251,15 +312,25 @@ def run_ours(args):
     k1_avg_ms = k1_ms / max(k1_n, 1)
     achieved = BYTES_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e9
     fp32_achieved = FLOPS_PER_CLIP * B / (k1_avg_ms * 1e-3) / 1e12
-    roofline = {"kernel": "stft_mel_v3_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+    # `bound` names the roof that binds this kernel.  The contract's vocabulary is "hbm" | "tensor"; neither is true here: the
+    # fused kernel performs 75 flop per algorithmic byte on the CUDA cores (ridge 11.5), so the top-level achieved / peak /
+    # frac are FP32 TFLOP/s against the nominal 148 SM x 128 lanes x 2 x 1.965 GHz, and `hbm` carries the fraction of the
+    # measured HBM peak that BASELINE.json's metric asks for beside it.
+    roofline = {"kernel": "stft_mel_v3_kernel", "bound": "fp32", "achieved": fp32_achieved, "peak": FP32_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": fp32_achieved / FP32_PEAK_TFLOPS,
+                "note": "68 MFLOP/clip (SURVEY 8d: 2.5 N log2 N FFT convention + window, power, banded mel) over the kernel's "
+                        "CUDA-event time; peak is nominal FP32 FMA issue (no measured FP32 figure in MEASURED_PEAKS.json)",
+                "traffic": traffic,
                 "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
                                 "in profiles/ (1024 clips per launch) scaled to this batch", "peak_kind": peak_kind,
                 "ms_per_launch": k1_avg_ms, "share_of_step": k1_avg_ms / (ms_total / args.steps),
-                "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B,
+                "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B, "algorithmic_flops_per_launch": FLOPS_PER_CLIP * B,
+                "hbm": {"achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                        "note": "904 320 algorithmic bytes per clip over the same time: what BASELINE.json's '% HBM roofline' "
+                                "asks; the FFT's arithmetic, not memory, bounds this kernel (SURVEY 8d: <= 15 % reachable)"},
+                # kept under its round-1 name for readers of older lines
                 "fp32": {"achieved": fp32_achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": fp32_achieved / FP32_PEAK_TFLOPS,
-                         "note": "binding roof: 68 MFLOP/clip of FP32 FFT work vs 0.9 MB of traffic (SURVEY 8d)"}}
+                         "frac": fp32_achieved / FP32_PEAK_TFLOPS}}
 
     # ---- e2e: host buffers through the public host API, copies inside the timed region --------------------------
     e2e = None
@@ -304,31 +375,43 @@ def run_ours(args):
                "api": "HostPipe.run (cacfe_hostpipe_run): pinned host -> H2D -> normalise/STFT/mel/PCEN -> D2H; "
                       f"{n_pipes} pipes on {n_pipes} host threads, each step copies its own batch in and out",
                "checksum": float(h_out[0][0, :4, :4].sum())}
-        if rank == 0 and world == 1:
-            # What the host link gives for exactly these two buffers (one batch up, one batch of features down, issued
-            # together on two streams; plumbing only, no kernels): the ceiling of any f32-in / f32-out end-to-end path.
-            d_up = torch.empty((B, CLIP), dtype=torch.float32, device=device)
-            d_dn = torch.ones((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, device=device)
-            s_up, s_dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        # What the host link gives for exactly these two buffers (one batch up, one batch of features down, issued together
+        # on two streams; plumbing only, no kernels), measured at EVERY N with all ranks copying at the same time: the
+        # ceiling of any f32-in / f32-out end-to-end path on this box at this N.  Per-rank rates and the NUMA node of each
+        # rank's pinned buffer and GPU go into the line so that the e2e scaling curve is attributed by measurement.
+        d_up = torch.empty((B, CLIP), dtype=torch.float32, device=device)
+        d_dn = torch.ones((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, device=device)
+        s_up, s_dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
 
-            def both():
-                with torch.cuda.stream(s_up):
-                    d_up.copy_(h_in[0], non_blocking=True)
-                with torch.cuda.stream(s_dn):
-                    h_out[0].copy_(d_dn, non_blocking=True)
+        def both():
+            with torch.cuda.stream(s_up):
+                d_up.copy_(h_in[0], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_out[0].copy_(d_dn, non_blocking=True)
 
+        both()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
             both()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                both()
-            torch.cuda.synchronize()
-            t_link = (time.perf_counter() - t0) / 3
-            e2e["link_ceiling"] = {"clips_per_s": B / t_link, "frac": e2e["value"] / (B / t_link),
-                                   "h2d_GBps": B * CLIP * 4 / t_link / 1e9,
-                                   "note": "one batch's H2D and D2H issued together from pinned memory, no kernels "
-                                           "(tools/probe_pcie.py): the host link bounds e2e, not the GPU"}
-            del d_up, d_dn
+        torch.cuda.synchronize()
+        t_mine = (time.perf_counter() - t0) / 3
+        t_link = dist_.max_over_ranks(t_mine, device)
+        mine = torch.tensor([B * CLIP * 4 / t_mine / 1e9, B * plan.n_frames * cfg.n_mels * 4 / t_mine / 1e9,
+                             float(numa_node_of(h_in[0].data_ptr())), float(gpu_numa_node(local))], dtype=torch.float64, device=device)
+        per_rank = [mine]
+        if world > 1:
+            per_rank = [torch.zeros_like(mine) for _ in range(world)]
+            torch.distributed.all_gather(per_rank, mine)
+        ceiling = world * B / t_link
+        e2e["link_ceiling"] = {"clips_per_s": ceiling, "frac": e2e["value"] / ceiling, "n_gpus": world,
+                               "h2d_GBps": world * B * CLIP * 4 / t_link / 1e9,
+                               "per_rank": [{"h2d_GBps": round(float(v[0]), 2), "d2h_GBps": round(float(v[1]), 2),
+                                             "pinned_numa_node": int(v[2]), "gpu_numa_node": int(v[3])} for v in per_rank],
+                               "host_threads": os.cpu_count(),
+                               "note": "every rank's H2D and D2H of one batch issued together from pinned memory, all ranks "
+                                       "at once, no kernels: the host side bounds e2e, not the GPU"}
+        del d_up, d_dn
         # Extension, reported beside the headline and never instead of it: the same run from 16-bit PCM host samples
         # (cacfe_hostpipe_run_pcm16: half the upload bytes, s / 32768 on the device, features bit-identical to the float32
         # call on the converted samples).  The reference's callables take float32, so `e2e.value` above stays the number.
@@ -396,9 +479,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, nb = cpu_reference_run(32, budget_s=15.0)
-        cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{nb} batches of 32 synthetic clips (configs[0]); oracle port of the reference's f32 op order, scipy pocketfft all workers"}
+        r = cpu_reference_run(32, budget_s=20.0)
+        cpu = {"value": r["value"], "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": CPU_SAMPLE.format(n=r["batches"], best=r["best"], tp=r["torch_port"], npp=r["numpy_port"], th=r["threads"]),
+               "torch_port": r["torch_port"], "numpy_port": r["numpy_port"]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
@@ -408,15 +492,53 @@ def run_ours(args):
                            "batch_per_gpu": B, "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (B * CLIP * 4 / 1e9),
                            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "other_rows": rows, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "checksum": float(out[0, :4, :4].sum())}
+                "clocks": clocks, "checksum": float(out[0, :4, :4].sum()), "rank_check": rank_check}
         args.emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
 
 
+def run_config45(args):
+    """BASELINE.json configs[3] / configs[4]: the front-end feeding its consumers on the device
+    -- `--config 4`: centred front-end -> badwinner2 inference (predict.py path); `--config 5`: raw_to_mel (C = 3) -> PCEN ->
+    wr_resnet_bird training step, one process per GPU (DDP over NCCL under torchrun).  The consumers are the torch
+    restatements of audio-training_b200/consumers.py (cuDNN, bf16 autocast; pinned against the executed reference graph by
+    tests/test_consumers.py), random weights.  `value` = end-to-end clips/s; the front-end's own rate and its share of the
+    step say whether it keeps the model fed.  Not the headline: configs[1] (no --config) is."""
+    import types
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import bench_configs as bc
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --config 4|5: no CUDA device")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+    a = types.SimpleNamespace(batch=args.batch if args.batch != 4096 else 64, steps=max(2, min(args.steps, 10)), labels=10)
+    res = (bc.config4 if args.config == 4 else bc.config5)(a, dev, world)
+    if int(os.environ.get("RANK", 0)) == 0:
+        ms = a.batch * world * 1e3 / res["end_to_end_clips_per_s"]
+        args.emit({"metric": METRIC + f" feeding the consumer of BASELINE config {args.config}", "value": res["end_to_end_clips_per_s"],
+                   "unit": "clips/s", "n_gpus": world, "steps": a.steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "f32 features, bf16 consumer", "data": "synthetic",
+                   "config": {"workload": res["config"], "batch_per_gpu": a.batch, "model": res["model"]},
+                   "frontend_clips_per_s": res["frontend_clips_per_s"], "model_clips_per_s": res["model_clips_per_s"],
+                   "frontend_share_of_step": res["frontend_share_of_step"], "frontend_over_model": res["frontend_over_model"]})
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="2: the headline (BASELINE.json configs[1]); 4 / 5: the front-end feeding badwinner2 inference / "
+                         "a wr_resnet_bird training step (reported, not the headline)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
@@ -444,6 +566,8 @@ def main():
     args.emit = emit
     if args.impl == "reference":
         return run_reference(args)
+    if args.config in (4, 5):
+        return run_config45(args)
     return run_ours(args)
 
 

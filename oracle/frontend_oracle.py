@@ -628,3 +628,27 @@ def reference_cpu_path(x, weights, workers=-1, with_pcen=True, channels=3):
     if with_pcen:
         return out, pcen(np.swapaxes(img, 1, 2), dtype=np.float32)
     return out, None
+
+
+def reference_cpu_path_torch(x, weights, with_pcen=True, channels=3):
+    """The same op order on torch's CPU kernels (MKL / pocketfft FFT, oneDNN sgemm, intra-op threads = torch.get_num_threads()):
+    the faster of the two faithful CPU ports on the boxes measured (3-4x the numpy / scipy form, which spends 40 % of its time
+    in a single-threaded fancy-index framing) and therefore the CPU baseline bench.py reports.  Float32 throughout; results
+    agree with reference_cpu_path to ~1e-5 relative (different FFT factorisation and summation order)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    t = t - t.min(-1, keepdim=True).values                                    # tfdataset.py:1916-1934, one op at a time
+    t = t / t.max(-1, keepdim=True).values + 0.000001
+    t = (t - 0.5) * 2
+    n = t.shape[-1]
+    n_frames = -(-n // HOP)
+    t = torch.nn.functional.pad(t, (0, max(0, N_FFT + HOP * (n_frames - 1) - n)))     # pad_end=True
+    win = torch.from_numpy(hann_periodic(N_FFT, np.float32))
+    z = torch.stft(t, N_FFT, HOP, N_FFT, window=win, center=False, return_complex=True)[..., :n_frames]   # [B, K, T]
+    p = (z ** 2).abs()                                                       # :2044-2046 (torch.stft is already [K, T])
+    w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float32)).unsqueeze(0).repeat(t.shape[0], 1, 1)   # :2049-2050
+    img = torch.bmm(w, p)                                                    # :2051 batch_dot
+    out = img.unsqueeze(-1).repeat(1, 1, 1, channels) if channels else img   # :2052-2053
+    if with_pcen:
+        return out.numpy(), pcen(img.transpose(1, 2).numpy(), dtype=np.float32)
+    return out.numpy(), None

@@ -7,7 +7,7 @@
 
 Reports front-end-only, model-only and end-to-end clips/s per configuration and whether the front-end keeps the model
 fed (front-end clips/s / model clips/s).  The models are torch restatements with random weights
-(audio-training_b200/consumers.py, parity unpinned); bf16 autocast, channels_last -- the consumer's precision is the
+(audio-training_b200/consumers.py, pinned against the executed reference graph by tests/test_consumers.py); bf16 autocast, channels_last -- the consumer's precision is the
 consumer's choice, the features stay FP32.  CUDA-event timed, max over ranks.
 
   python tools/bench_configs.py [--config 4|5|all] [--batch N] [--steps K]
