@@ -1229,7 +1229,7 @@ int cacfe_sosfilt(cacfe_plan* p, const double* sos_host, int n_sections, const f
     return fail(CACFE_EINVAL, "sosfilt: 1..%d sections supported (got %d)", cacfe::kSosMaxSections, n_sections);
   if (rows < 1 || n < 1) return fail(CACFE_ESHAPE, "sosfilt: bad shape");
   CUDA_TRY(cudaSetDevice(p->device));
-  cacfe::SosArgs a{};
+  thread_local cacfe::SosArgs a;   // 9 KB of kernel parameters, staged per host thread
   a.in = in;
   a.out = out;
   a.rows = rows;
@@ -1238,9 +1238,29 @@ int cacfe_sosfilt(cacfe_plan* p, const double* sos_host, int n_sections, const f
   for (int s = 0; s < n_sections; ++s) {
     const double a0 = sos_host[6 * s + 3];
     if (a0 == 0.0) return fail(CACFE_EINVAL, "sosfilt: a0 == 0 in section %d", s);
-    for (int c = 0; c < 6; ++c) a.sos[s][c] = sos_host[6 * s + c] / a0;  // scipy normalises by a0 as well
+    cacfe::SosSection& q = a.sec[s];
+    q.b0 = sos_host[6 * s + 0] / a0;   // scipy normalises by a0 as well
+    q.b1 = sos_host[6 * s + 1] / a0;
+    q.b2 = sos_host[6 * s + 2] / a0;
+    q.a1 = sos_host[6 * s + 4] / a0;
+    q.a2 = sos_host[6 * s + 5] / a0;
+    q.c1 = q.b1 - q.a1 * q.b0;
+    q.c2 = q.b2 - q.a2 * q.b0;
+    // P = A^32 with A = [[-a1, 1], [-a2, 0]] and its powers 0..32, in long double
+    long double A[4] = {-(long double)q.a1, 1.0L, -(long double)q.a2, 0.0L}, P[4] = {1.0L, 0.0L, 0.0L, 1.0L};
+    auto mul = [](const long double* x, const long double* y, long double* z) {
+      const long double r[4] = {x[0] * y[0] + x[1] * y[2], x[0] * y[1] + x[1] * y[3], x[2] * y[0] + x[3] * y[2], x[2] * y[1] + x[3] * y[3]};
+      for (int i = 0; i < 4; ++i) z[i] = r[i];
+    };
+    for (int i = 0; i < cacfe::kSosRun; ++i) mul(P, A, P);
+    long double M[4] = {1.0L, 0.0L, 0.0L, 1.0L};
+    for (int m = 0; m <= cacfe::kSosRun; ++m) {
+      for (int i = 0; i < 4; ++i) q.pw[m][i] = (double)M[i];
+      mul(M, P, M);
+    }
   }
-  cacfe::sosfilt_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(a);
+  if (rows > 2147483647LL) return fail(CACFE_ESHAPE, "sosfilt: too many rows for one launch");
+  cacfe::sosfilt_scan_kernel<<<(unsigned)rows, cacfe::kSosThreads, 0, (cudaStream_t)stream>>>(a);
   return check_launch(p, "sosfilt");
 }
 

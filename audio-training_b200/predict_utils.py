@@ -61,10 +61,11 @@ def get_spect(data, sr, hop_length, mean_sub, use_mfcc, mel_break, htk, n_mels, 
 
 
 def window_table(n_frames, sr, tracks, segment_length=3, stride=1, fmin=100, fmax=11000, pad_short_tracks=False,
-                 randint=None):
+                 randint=None, segments=None):
     """The integer window arithmetic of load_samples (predict_utils.py:53-147), bit for bit, without touching audio.
     -> list[track] of list[(src_start, src_len, pad_left)].  `randint(0, extra)` is np.random.randint by default
-    (the reference pads short windows at a random offset, :116-119)."""
+    (the reference pads short windows at a random offset, :116-119).  `segments` (a list) receives per track the
+    (start, length) of the reference's `track_frames` slice, or None for a track outside the band."""
     randint = randint or np.random.randint
     sample_size = int(sr * segment_length)
     table = []
@@ -72,6 +73,8 @@ def window_table(n_frames, sr, tracks, segment_length=3, stride=1, fmin=100, fma
         rows = []
         table.append(rows)
         if t.freq_start is not None and t.freq_end is not None and (t.freq_start > fmax or t.freq_end < fmin):
+            if segments is not None:
+                segments.append(None)
             continue  # track entirely outside the band: empty list (:61-68)
         clock = 0
         first = int(sr * t.start)
@@ -94,6 +97,8 @@ def window_table(n_frames, sr, tracks, segment_length=3, stride=1, fmin=100, fma
                     assert last - first == sample_size
         seg_lo = min(max(first, 0), n_frames)            # frames[first:last] slice semantics
         seg_len = min(max(last, seg_lo), n_frames) - seg_lo
+        if segments is not None:
+            segments.append((seg_lo, seg_len))
         a, b = 0, min(last, sample_size)                  # :101-102 -- absolute index vs length, kept (Q11)
         while True:
             lo = min(a, seg_len)
@@ -119,13 +124,12 @@ def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=281,
     [fmin, fmax]).  One batched GPU launch for every window of every track."""
     logging.info("Loading samples with length %s stride %s hop length %s n mels %s fmin %s fmax %s n_fft %s",
                  segment_length, stride, hop_length, n_mels, fmin, fmax, n_fft)
-    if filter_freqs or filter_below:
-        raise NotImplementedError("load_samples: Butterworth pre-filtering is off in every reference caller and is not built")
     if not htk or use_mfcc or mean_sub:
         raise NotImplementedError("load_samples: htk=False / use_mfcc / mean_sub are not built")
     frames = np.asarray(frames)
     size = int(sr * segment_length)
-    table = window_table(len(frames), sr, tracks, segment_length, stride, fmin, fmax, pad_short_tracks, randint)
+    segments = []
+    table = window_table(len(frames), sr, tracks, segment_length, stride, fmin, fmax, pad_short_tracks, randint, segments)
     flat = [w for rows in table for w in rows]
     if not flat:
         return [[] for _ in table]
@@ -135,6 +139,22 @@ def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=281,
     for i, (s0, n, left) in enumerate(flat):
         view[i, left:left + n] = frames[s0:s0 + n]
     dev = batch.to(f"cuda:{device}", non_blocking=True)
+    if filter_freqs or filter_below:
+        # predict_utils.py:103-113: the whole track segment goes through a Butterworth band-pass (order 2, the track's own
+        # freq_start..freq_end; low-pass when freq_start <= 0) before it is cut into windows.  The segment is filtered on the
+        # device (cacfe_sosfilt: scipy's float64 recurrence, parallel in time) and its windows overwrite the unfiltered rows.
+        from scipy.signal import butter
+        row = 0
+        for t, rows, seg in zip(tracks, table, segments):
+            if rows and (filter_freqs or t.freq_end < filter_below):
+                nyq = 0.5 * sr                                   # butter_bandpass, predict_utils.py:245-256
+                fr = ([t.freq_start / nyq] if t.freq_start > 0 else []) + [t.freq_end / nyq]
+                sos = butter(2, fr, analog=False, btype="bandpass" if t.freq_start > 0 else "lowpass", output="sos")
+                track = torch.from_numpy(np.ascontiguousarray(frames[seg[0]:seg[0] + seg[1]], dtype=np.float32))
+                filt = rt.get_plan(rt.FrontendConfig(), device).sosfilt(sos, track.to(f"cuda:{device}").unsqueeze(0))[0]
+                for k, (s0, n, left) in enumerate(rows):
+                    dev[row + k, left:left + n] = filt[s0 - seg[0]:s0 - seg[0] + n]
+            row += len(rows)
     plan = _spect_plan(size, sr, hop_length, mel_break, n_mels, fmin, fmax, n_fft, power, channels, normalize, device,
                        pad_mode)
     feats = plan.frontend(dev)

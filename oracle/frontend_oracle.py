@@ -428,12 +428,13 @@ class Track:
 
 
 def load_samples_windows(n_frames, sr, tracks, segment_length=3, stride=1, fmin=FMIN, fmax=FMAX,
-                         pad_short_tracks=False, rand_offset=None):
+                         pad_short_tracks=False, rand_offset=None, segments=None):
     """Integer window arithmetic of predict_utils.load_samples (:53-147), no features.
 
     Returns list[track] of list[(src_start, src_len, pad_left)]: window = `src_len` samples of the
     recording starting at `src_start`, placed at `pad_left` inside a zero buffer of `sample_size`.
-    `rand_offset(extra)` stands in for np.random.randint(0, extra) (:118)."""
+    `rand_offset(extra)` stands in for np.random.randint(0, extra) (:118).  `segments` (a list) receives
+    per track the (start, length) of `track_frames = frames[sr_start:sr_end]` (:77, :99), or None."""
     if rand_offset is None:
         rand_offset = lambda extra: 0  # noqa: E731
     sample_size = int(sr * segment_length)
@@ -443,6 +444,8 @@ def load_samples_windows(n_frames, sr, tracks, segment_length=3, stride=1, fmin=
         if (t.freq_start is not None and t.freq_end is not None
                 and (t.freq_start > fmax or t.freq_end < fmin)):  # :61-68
             out.append(wins)
+            if segments is not None:
+                segments.append(None)
             continue
         start = 0
         s_end = int(t.end * sr)
@@ -465,6 +468,8 @@ def load_samples_windows(n_frames, sr, tracks, segment_length=3, stride=1, fmin=
         lo = min(max(s_start, 0), n_frames)
         hi = min(max(s_end, lo), n_frames)
         base, base_len = lo, hi - lo
+        if segments is not None:
+            segments.append((base, base_len))
         w_start = 0
         w_end = min(s_end, sample_size)  # :101-102 (Q11: absolute index vs length)
         while True:  # :114-147
@@ -489,19 +494,29 @@ def load_samples_windows(n_frames, sr, tracks, segment_length=3, stride=1, fmin=
 def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=HOP,
                  mel_break=BREAK_FREQ, n_mels=N_MELS, fmin=FMIN, fmax=FMAX, channels=1, power=2,
                  db_scale=False, normalize_clip=True, n_fft=N_FFT, pad_short_tracks=False,
-                 rand_offset=None, pad_mode="constant", dtype=np.float64):
-    """predict_utils.load_samples (:9-150), default branches, on top of the window table."""
+                 rand_offset=None, pad_mode="constant", dtype=np.float64, filter_freqs=False, filter_below=None):
+    """predict_utils.load_samples (:9-150), default branches, on top of the window table; `filter_freqs` /
+    `filter_below` band-pass the whole track segment first (:103-113: butter order 2 between the track's
+    freq_start and freq_end, scipy sosfilt in f64 -- the filtered track stays f64 in the reference)."""
+    from scipy.signal import butter, sosfilt
     frames = np.asarray(frames)
     size = int(sr * segment_length)
     result = []
-    for wins in load_samples_windows(len(frames), sr, tracks, segment_length, stride, fmin, fmax,
-                                     pad_short_tracks, rand_offset):
+    segs = []
+    table = load_samples_windows(len(frames), sr, tracks, segment_length, stride, fmin, fmax, pad_short_tracks, rand_offset, segs)
+    for t, wins, seg in zip(tracks, table, segs):
         feats = []
+        src, shift = frames, 0
+        if seg is not None and (filter_freqs or (filter_below and t.freq_end < filter_below)):
+            nyq = 0.5 * sr                                          # predict_utils.butter_bandpass (:245-256)
+            fr = ([t.freq_start / nyq] if t.freq_start > 0 else []) + [t.freq_end / nyq]
+            sos = butter(2, fr, analog=False, btype="bandpass" if t.freq_start > 0 else "lowpass", output="sos")
+            src, shift = sosfilt(sos, frames[seg[0]:seg[0] + seg[1]]), seg[0]
         for (s0, n, left) in wins:
-            data = np.zeros(size, dtype=frames.dtype)
-            data[left:left + n] = frames[s0:s0 + n]
+            data = np.zeros(size, dtype=src.dtype)
+            data[left:left + n] = src[s0 - shift:s0 - shift + n]
             if normalize_clip:
-                data = normalize(data, dtype=np.float32 if frames.dtype == np.float32 else np.float64)
+                data = normalize(data, dtype=np.float32 if src.dtype == np.float32 else np.float64)
             feats.append(get_spect(data, sr, hop_length, mel_break, n_mels, fmin, fmax, n_fft, power,
                                    db_scale, channels, pad_mode, dtype))
         result.append(feats)

@@ -538,6 +538,50 @@ def test_load_data_against_reference_golden(oracle):
     assert mel.shape == (160, fields["audio/spectogram"].size // 2049, 1) and np.isfinite(mel).all()
 
 
+def test_sosfilt_parallel_scan_against_scipy():
+    """cacfe_sosfilt (sosfilt_scan_kernel: scipy's float64 recurrence cut into 32-sample runs whose start states come from a
+    scan of affine maps) against scipy.signal.sosfilt: float32 results equal except where the float64 value sits on a rounding
+    boundary (<= 1 ulp, a vanishing fraction).  Low-pass / band-pass / high-order filters, rows that are unaligned, shorter than a
+    run, not multiples of 4 or of the 8192-sample tile, and one long recording (352 tiles through one CTA)."""
+    from scipy.signal import butter, sosfilt
+    rng = np.random.default_rng(17)
+    plan = rt.get_plan(rt.FrontendConfig(), 0)
+    filters = [butter(2, 3000 / 24000, btype="lowpass", output="sos"), butter(2, [800 / 24000, 5000 / 24000], btype="bandpass", output="sos"),
+               butter(8, [300 / 24000, 11000 / 24000], btype="bandpass", output="sos"), butter(3, 0.9, btype="highpass", output="sos")]
+    shapes = [(5, 144000), (3, 8192), (2, 8193), (4, 31), (3, 1001), (1, 60 * 48000 + 2), (2, 16384)]
+    for sos in filters:
+        for shape in shapes:
+            x = (rng.standard_normal(shape) * 0.3 + 0.1).astype(np.float32)
+            got = plan.sosfilt(sos, torch.from_numpy(x).cuda()).cpu().numpy()
+            want = sosfilt(sos, x.astype(np.float64), axis=-1)
+            w32 = want.astype(np.float32)
+            ulp = np.spacing(np.abs(w32)) 
+            assert np.all(np.abs(got.astype(np.float64) - want) <= 1.0001 * ulp.astype(np.float64)), (len(sos), shape)
+            assert np.mean(got != w32) < 1e-4, (len(sos), shape, float(np.mean(got != w32)))
+    flat = torch.from_numpy((rng.standard_normal(3 * 5000 + 1)).astype(np.float32)).cuda()[1:].view(3, 5000)   # 4-byte aligned rows
+    got = plan.sosfilt(filters[1], flat).cpu().numpy()
+    assert np.array_equal(got, sosfilt(filters[1], flat.cpu().numpy().astype(np.float64), axis=-1).astype(np.float32)) or \
+        np.mean(got != sosfilt(filters[1], flat.cpu().numpy().astype(np.float64), axis=-1).astype(np.float32)) < 1e-4
+
+
+def test_load_samples_with_track_filter(oracle):
+    """load_samples(filter_freqs=True / filter_below=...) (predict_utils.py:103-115): the track's band-pass on the device, against
+    the features the reference code produced (tests/golden/load_samples_filter.npz) and the f64 oracle."""
+    g = np.load(os.path.join(GOLDEN, "load_samples_filter.npz"))
+    frames = oracle.synth_recording(float(g["params"][0]), seed=int(g["params"][1]))
+    tracks = [oracle.Track(*t) for t in g["tracks"]]
+    for tag, kw in (("filter_freqs", dict(filter_freqs=True)), ("filter_below", dict(filter_below=6000))):
+        got = atb.load_samples(frames, 48000, tracks, randint=lambda lo, hi: 0, **kw)
+        want = oracle.load_samples(frames, 48000, tracks, dtype=np.float64, **kw)
+        assert [len(r) for r in got] == list(g[f"{tag}_counts"])
+        flat = [w for r in got for w in r]
+        for a, b in zip(flat, [w for r in want for w in r]):
+            check(oracle, a, b, 2.0, what=f"load_samples {tag} vs f64 oracle")
+        sub = np.stack([w[::7, ::19, 0] for w in flat])
+        ok, worst = oracle.within_tolerance(sub, g[f"{tag}_sub"], 2e-4, 2e-5)
+        assert ok, (tag, worst)
+
+
 # ------------------------------------------------------------------------------------------------ a15 variants
 def test_multi_resolution_variants(oracle, golden_banks, xn):
     """raw_to_mel_rgb / raw_to_mel_dual (tfdataset.py:1818-2004): 1024- and 2048-point STFTs through the 4096-point kernel

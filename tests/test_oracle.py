@@ -315,3 +315,22 @@ def test_signal_noise_oracle_against_reference_golden(oracle):
         assert np.isclose(float(spec.astype(np.float64).sum()), float(g[f"spec_sum_{tag}"][0]), rtol=1e-9)
         assert sig.shape == g[f"signals_{tag}"].shape and len(sig) >= 8
         assert np.array_equal(sig, g[f"signals_{tag}"])
+
+
+def test_filtered_load_samples_matches_reference_code(oracle):
+    """predict_utils.load_samples with its Butterworth pre-filter (predict_utils.py:103-115), executed from the reference
+    source over the stand-ins (tests/golden/load_samples_filter.npz), against the oracle's restatement."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "load_samples_filter.npz"))
+    frames = oracle.synth_recording(float(g["params"][0]), seed=int(g["params"][1]))
+    tracks = [oracle.Track(*t) for t in g["tracks"]]
+    for tag, kw in (("filter_freqs", dict(filter_freqs=True)), ("filter_below", dict(filter_below=6000))):
+        res = oracle.load_samples(frames, 48000, tracks, dtype=np.float32, **kw)
+        assert [len(r) for r in res] == list(g[f"{tag}_counts"])
+        flat = [w for r in res for w in r]
+        sub = np.stack([w[::7, ::19, 0] for w in flat])
+        assert np.allclose(sub, g[f"{tag}_sub"], rtol=2e-5, atol=1e-7 * float(g[f"{tag}_sub"].max()))
+        assert np.allclose([w.sum(dtype=np.float64) for w in flat], g[f"{tag}_sum"], rtol=1e-5)
+    plain = oracle.load_samples(frames, 48000, tracks, dtype=np.float32)
+    assert not np.allclose(plain[0][0], res[0][0], rtol=1e-2)          # the filter does something

@@ -61,4 +61,7 @@ ns = min(B, 1024)
 report("stft -> stored spectrogram [B,2049,T]", timed(lambda: st.stft(x[:ns]), 5), ns * (N * 4 + 2049 * T * 4), ns)
 import numpy as np
 sos = np.array([[0.02995458, 0.05990916, 0.02995458, 1.0, -1.45424359, 0.57406192]])
-report("sosfilt (order-2 low-pass, FP64 recurrence)", timed(lambda: plan.sosfilt(sos, x[:256]), 3), 256 * N * 8, 256)
+report("sosfilt (order-2 low-pass: 1 section, FP64 parallel scan)", timed(lambda: plan.sosfilt(sos, x), 5), B * N * 8, B)
+from scipy.signal import butter
+bp = butter(2, [800 / 24000, 5000 / 24000], btype="bandpass", output="sos")
+report("sosfilt (order-2 band-pass: 2 sections)", timed(lambda: plan.sosfilt(bp, x), 5), B * N * 8, B)

@@ -10,13 +10,25 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+EXTRA = re.compile(r"(sm__pipe_tensor|sm__inst_executed_pipe_t(ensor|mem|c)|sm__ops_path_tensor.*tf32.*pct|tmem|utc)", re.I)
 for vals in rows[2:]:
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     print("==", d.get("Kernel Name", ("?", ""))[0])
     for k in KEYS:
         if k in d:
             print("  ", k, d[k])
+    for h in sorted(d):     # every tensor-pipe / TMEM metric the report carries that is not zero
+        if EXTRA.search(h) and h not in KEYS and ("pct" in h or h.endswith(".sum")):
+            try:
+                if float(d[h][0].replace(",", "")) != 0.0:
+                    print("  ", h, d[h])
+            except ValueError:
+                pass
     try:
         t = float(d["gpu__time_duration.sum"][0].replace(",", ""))
         tu = d["gpu__time_duration.sum"][1]
