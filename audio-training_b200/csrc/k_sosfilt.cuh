@@ -96,9 +96,12 @@ __global__ void __launch_bounds__(kSosThreads, 2) sosfilt_scan_kernel(const __gr
         z1 = n1;
       }
       // the carry of the previous tile enters through thread 0:  c_0 += P s_carry
+      double carry1 = 0.0, carry2 = 0.0;                   // thread 0: the state the previous tile ended in = its own start state
       if (tid == 0) {
+        carry1 = s_carry[s][0];
+        carry2 = s_carry[s][1];
         double m[4] = {q.pw[1][0], q.pw[1][1], q.pw[1][2], q.pw[1][3]}, p1, p2;
-        sos_apply(m, s_carry[s][0], s_carry[s][1], p1, p2);
+        sos_apply(m, carry1, carry2, p1, p2);
         z1 += p1;
         z2 += p2;
       }
@@ -135,8 +138,8 @@ __global__ void __launch_bounds__(kSosThreads, 2) sosfilt_scan_kernel(const __gr
       {
         double m[4] = {q.pw[lane][0], q.pw[lane][1], q.pw[lane][2], q.pw[lane][3]}, p1, p2;
         sos_apply(m, w1, w2, p1, p2);                      // P^lane E_w
-        z1 = e1 + p1;
-        z2 = e2 + p2;
+        z1 = e1 + p1 + carry1;                             // (the carry is already inside every later run's end state)
+        z2 = e2 + p2 + carry2;
       }
       // 3. the run again from its true start state, scipy's operation sequence; the last thread leaves the tile's carry
 #pragma unroll

@@ -219,3 +219,30 @@ dist.destroy_process_group()
                          capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "GATHER_OK" in res.stdout
+
+
+def _shim_tf():
+    sys.path.insert(0, os.path.join(REPO, "oracle", "ref_shim"))
+    import tf_numpy
+    return tf_numpy
+
+
+def test_keras_layer_adapter_keeps_the_reference_weights(golden):
+    """keras_layers.make_layers(tf): real Layer subclasses (here over the numpy stand-in for tf.keras.layers.Layer) with the
+    reference's weight names, creation order and initial values (tfpcen.py:15-19,48-87; badwinner2.py:36-45)."""
+    from audio_training_b200.keras_layers import make_layers
+    tf = _shim_tf()
+    L = make_layers(tf)
+    layer = L.PCEN()
+    assert isinstance(layer, tf.keras.layers.Layer) and isinstance(layer.ema, tf.keras.layers.Layer)
+    names = [n for n, _ in layer._added] + ["EMA/" + n for n, _ in layer.ema._added]
+    assert sorted(names) == sorted(golden["pcen_weight_names"])
+    assert [n for n, _ in layer._added] == ["gain", "bias", "root", "a-power"] and layer.ema.name == "EMA"
+    vals = dict(zip(golden["pcen_weight_names"], golden["pcen_weight_values"]))
+    for n, v in layer._added:
+        assert float(v[0]) == np.float32(vals[n])
+    assert float(layer.ema._added[0][1][0]) == np.float32(vals["EMA/smooth"])
+    assert layer.get_config()["norm_scope"] == "tensor"
+    mag = L.MagTransform()
+    assert [n for n, _ in mag._added] == ["a-power"] and float(mag._added[0][1][0]) == -1.0
+    assert L.ExponentialMovingAverage(0.04, True).get_config() == {"coeff_init": 0.04, "trainable": True}
