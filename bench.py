@@ -499,6 +499,87 @@ def run_ours(args):
     return 0
 
 
+def synth_keyed(torch, indices, device, seed=20240):
+    """SURVEY 8d generator with a counter-based RNG keyed (seed, global clip index): clip i is the same whichever rank and
+    whichever chunk it lands in.  indices: int64 tensor [n] on `device` -> float32 [n, CLIP]."""
+    def u01(ctr):                                   # splitmix64-style integer hash -> uniform [0, 1) (int64 wrap-around is intended)
+        z = ctr * -7046029254386353131              # 0x9E3779B97F4A7C15 as int64
+        z = (z ^ (z >> 30 & 0x3FFFFFFFF)) * -4658895280553007687
+        z = (z ^ (z >> 27 & 0x1FFFFFFFFF)) * -7723592293110705685
+        z = z ^ (z >> 31 & 0x1FFFFFFFF)
+        return ((z >> 11) & 0x1FFFFFFFFFFFFF).to(torch.float64) * (1.0 / 9007199254740992.0)
+
+    if indices.numel() > 512:                       # the int64 counters are 8 bytes per sample: generate 512 clips at a time
+        return torch.cat([synth_keyed(torch, indices[i:i + 512], device, seed) for i in range(0, indices.numel(), 512)])
+    n = indices.numel()
+    key = (indices.to(torch.int64) + seed * 1000003).view(n, 1)
+    col = torch.arange(CLIP, device=device, dtype=torch.int64).view(1, CLIP)
+    x = (0.3 * (2.0 * u01(key * 262144 * 4 + col) - 1.0)).float()
+    t = torch.arange(CLIP, device=device, dtype=torch.float64) / 48000.0
+    p = u01(key * 262144 * 4 + 1000000 + torch.arange(10, device=device, dtype=torch.int64).view(1, 10))      # 10 parameters per clip
+    for j in range(3):
+        a = 0.05 + 0.45 * p[:, 3 * j:3 * j + 1]
+        f0 = 300.0 + 10700.0 * p[:, 3 * j + 1:3 * j + 2]
+        f1 = 300.0 + 10700.0 * p[:, 3 * j + 2:3 * j + 3]
+        x += (a * torch.sin(2.0 * np.pi * (f0 * t[None] + 0.5 * ((f1 - f0) / 3.0) * t[None] ** 2))).float()
+    x += (0.2 * p[:, 9:10] - 0.1).float()
+    return x.contiguous()
+
+
+def run_corpus(args):
+    """BASELINE.json configs[2] as SURVEY 8d writes it: a corpus of `--corpus` distinct synthetic clips, clip i -> rank i mod R,
+    processed in chunks of `--batch` clips generated on the device from the keyed generator (generation outside the timed
+    region: CUDA events bracket only the front-end steps), per-clip PCEN scope so that a clip's features do not depend on how the
+    corpus was sharded.  Every rank folds an exact per-clip checksum (sum of the feature bits) into an order-independent corpus
+    checksum; rank 0 all-reduces it, and prints it: the same corpus gives the same number at every N."""
+    import torch
+    from audio_training_b200 import _runtime as rt
+    from audio_training_b200 import distributed as dist_
+    rank, world, local = dist_.init()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    B = min(args.batch, 4096)
+    mine = torch.arange(rank, args.corpus, world, dtype=torch.int64, device=device)      # clip i -> rank i mod R
+    cfg = rt.FrontendConfig(normalize=True, channels=1, out_layout="btm")
+    plan = rt.get_plan(cfg, local)
+    params = rt.pcen_params(norm_scope="clip")
+    out = torch.empty((B, plan.n_frames, cfg.n_mels), dtype=torch.float32, device=device)
+    plan.frontend_pcen(synth_keyed(torch, mine[:min(B, mine.numel())], device), params, out[:min(B, mine.numel())])   # warm-up
+    total_ms, clips, launches0 = 0.0, 0, plan.launch_count()
+    csum = torch.zeros(1, dtype=torch.int64, device=device)
+    if world > 1:
+        torch.distributed.barrier()
+    for c0 in range(0, mine.numel(), B):
+        idx = mine[c0:c0 + B]
+        x = synth_keyed(torch, idx, device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        plan.frontend_pcen(x, params, out[:idx.numel()])
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        clips += idx.numel()
+        per_clip = out[:idx.numel()].view(torch.int32).view(idx.numel(), -1).sum(dim=1, dtype=torch.int64)
+        csum += (per_clip * (2 * idx + 1)).sum()          # weighted by the global index: a swapped pair of clips shows
+        del x
+    launches = plan.launch_count() - launches0
+    ms = dist_.max_over_ranks(total_ms, device)
+    if world > 1:
+        torch.distributed.all_reduce(csum)
+    if rank == 0:
+        args.emit({"metric": METRIC + ", 1 M-clip corpus sharded over the GPUs", "value": args.corpus / (ms * 1e-3), "unit": "clips/s",
+                   "n_gpus": world, "steps": -(-mine.numel() // B), "warmup": 1, "ms_per_step": ms / max(1, -(-mine.numel() // B)),
+                   "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": f"corpus of {args.corpus} distinct keyed synthetic clips, clip i -> rank i mod {world}, chunks of "
+                                          f"{B} generated on the device (untimed), fused normalize -> STFT -> mel -> PCEN (per-clip min-max)",
+                              "parallelism": f"{world} GPU(s), no data-path collective"},
+                   "corpus_checksum": int(csum.item()), "gpu_launches": int(launches)})
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def run_config45(args):
     """BASELINE.json configs[3] / configs[4]: the front-end feeding its consumers on the device
     -- `--config 4`: centred front-end -> badwinner2 inference (predict.py path); `--config 5`: raw_to_mel (C = 3) -> PCEN ->
@@ -536,9 +617,10 @@ def run_config45(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
-                    help="2: the headline (BASELINE.json configs[1]); 4 / 5: the front-end feeding badwinner2 inference / "
-                         "a wr_resnet_bird training step (reported, not the headline)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="2: the headline (BASELINE.json configs[1]); 3: a corpus of --corpus distinct clips sharded i mod R; "
+                         "4 / 5: the front-end feeding badwinner2 inference / a wr_resnet_bird training step (reported, not the headline)")
+    ap.add_argument("--corpus", type=int, default=1000000, help="clips of the --config 3 corpus")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
@@ -566,6 +648,8 @@ def main():
     args.emit = emit
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 3:
+        return run_corpus(args)
     if args.config in (4, 5):
         return run_config45(args)
     return run_ours(args)
