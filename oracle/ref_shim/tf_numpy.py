@@ -29,9 +29,14 @@ def _f32(x):
 
 # ---- tf.signal ------------------------------------------------------------------------
 def hann_window(window_length, periodic=True, dtype=np.float32, name=None):
-    n = np.arange(window_length, dtype=np.float64)
+    """tf.signal.hann_window (window_ops._raised_cosine_window): every step in `dtype` -- the sample index, 2 pi, the
+    division and the cosine are float32 operations, which is what TF executes (round 1 evaluated in float64 and rounded
+    once: up to 1 ulp of float32 apart from this)."""
+    dt = np.dtype(dtype).type
     denom = window_length if (periodic and window_length % 2 == 0) else window_length - 1
-    return (0.5 - 0.5 * np.cos(2.0 * np.pi * n / denom)).astype(np.float32)
+    count = np.arange(window_length).astype(dt)
+    cos_arg = dt(2.0 * np.pi) * count / dt(denom)
+    return (dt(0.5) - dt(0.5) * np.cos(cos_arg)).astype(dt)
 
 
 def frame(signal, frame_length, frame_step, pad_end=False, pad_value=0, axis=-1, name=None):
