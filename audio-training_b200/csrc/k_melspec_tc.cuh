@@ -22,7 +22,7 @@
 // HBM bound: 930 rows x 513 x 4 B in, 160 x 513 x 4 B out per clip.
 // Measured alternatives (384 clips): this kernel (A in shared memory, 32-bin chunks, 2 stages, 2 CTAs/SM) 0.370 ms; one
 // CTA/SM with 4 stages 0.584 ms; A operand written to TENSOR MEMORY by the producers (tcgen05.st, tcgen05.mma with
-// [a_tmem]; 16-bin chunks, 3 stages, 256 TMEM columns, 2 CTAs/SM -- kept as tools/k_melspec_tc_tmemA.cuh.txt) 0.467 ms.
+// [a_tmem]; 16-bin chunks, 3 stages, 256 TMEM columns, 2 CTAs/SM -- in the history: git show 49ad234:tools/k_melspec_tc_tmemA.cuh.txt) 0.467 ms.
 // Time per chunk scales with the chunk's bytes in all of them: the limit is DRAM efficiency on 412-byte row pieces at a
 // 2052-byte pitch (the banded FP32 kernel tops out at 1.6 TB/s on the same pattern), not the tensor pipe or the hand-over.
 #pragma once
