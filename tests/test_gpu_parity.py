@@ -783,6 +783,38 @@ def test_full_size_properties(oracle, bank):
     torch.cuda.empty_cache()
 
 
+def test_threads_share_one_cached_plan(oracle):
+    """The tf.data num_parallel_calls pattern: several host threads call the operators of ONE cached plan at once (ctypes
+    releases the GIL inside the C calls, which are multi-launch sequences passing per-clip statistics through a workspace).
+    The mirror keeps a workspace per (thread, stream): every thread must get exactly what it gets alone."""
+    import threading
+    plan = rt.get_plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
+    xs = [torch.from_numpy(oracle.synth_clips(np.arange(100 + 8 * k, 100 + 8 * k + 8)) * (1.0 + 0.3 * k) + 0.05 * k).cuda() for k in range(4)]
+    alone = [(plan.frontend(x).clone(), plan.frontend_pcen(x).clone(), plan.normalize(x).clone()) for x in xs]
+    torch.cuda.synchronize()
+    bad = []
+
+    def work(k):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(25):
+                a, b, c = plan.frontend(xs[k]), plan.frontend_pcen(xs[k]), plan.normalize(xs[k])
+                s.synchronize()
+                if not (torch.equal(a, alone[k][0]) and torch.equal(b, alone[k][1]) and torch.equal(c, alone[k][2])):
+                    bad.append(k)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not bad, f"threads {sorted(set(bad))} saw another thread's statistics"
+    with pytest.raises(ValueError):                      # a wrong-shaped `out=` must not reach the kernels
+        plan.frontend(xs[0], out=torch.empty((8, 513, 161), device="cuda"))
+    with pytest.raises(ValueError):
+        plan.frontend_pcen(xs[0][:, :1000])
+
+
 def test_errors():
     plan = rt.get_plan(rt.FrontendConfig(), 0)
     with pytest.raises(ValueError):
