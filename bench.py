@@ -301,7 +301,10 @@ def run_ours(args):
     traffic = None
     try:
         import re
-        txt = open(os.path.join(REPO, "profiles", "r01_k1_v5_ncu_summary.txt")).read()
+        # round-2 capture (tools/ncu_target_r2.py): the first kernel block of the digest is stft_mel_v3_kernel at 1024 clips
+        txt = open(os.path.join(REPO, "profiles", "r02_kernels_ncu_summary.txt")).read()
+        txt = txt[txt.index("stft_mel_v3_kernel"):]
+        txt = txt[:txt.index("\n== ")]
         rd = float(re.search(r"dram__bytes_read\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
         wr = float(re.search(r"dram__bytes_write\.sum \('([0-9.]+)', 'Mbyte'\)", txt).group(1))
         traffic = (rd + wr) * 1e6 / 1024.0 * B
@@ -322,7 +325,8 @@ def run_ours(args):
                         "CUDA-event time; peak is nominal FP32 FMA issue (no measured FP32 figure in MEASURED_PEAKS.json)",
                 "traffic": traffic,
                 "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture "
-                                "in profiles/ (1024 clips per launch) scaled to this batch", "peak_kind": peak_kind,
+                                "profiles/r02_kernels_ncu_summary.txt (1024 clips per launch) scaled to this batch; a profiler "
+                                "counter cannot be read in an un-profiled run", "peak_kind": peak_kind,
                 "ms_per_launch": k1_avg_ms, "share_of_step": k1_avg_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B, "algorithmic_flops_per_launch": FLOPS_PER_CLIP * B,
                 "hbm": {"achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
