@@ -645,8 +645,10 @@ int cacfe_normalize(cacfe_plan* p, const float* in, float* out, long long rows, 
 static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, int layout, int channels, void* ws,
                            cudaStream_t st, float* staging = nullptr) {
   if (!p->frontend_ok && !p->v3_ok)
-    return fail(CACFE_EINVAL, "frontend: n_fft=%d is not served by the fused kernels (4096; 512..2048 through the persistent "
-                "kernel, which needs n_samples %% 4 == 0 and a bank of at most 192 bands)", p->cfg.n_fft);
+    return fail(CACFE_EINVAL, "frontend: n_fft=%d hop=%d n_mels=%d is not served by the fused kernels: they take n_fft 4096 "
+                "(512..2048 through the persistent kernel, which needs n_samples %% 4 == 0 and a bank of at most 192 bands) and a "
+                "frame tile of 4096 + 11 hop samples that fits shared memory next to the tables (hop <= ~430 at 192 bands)",
+                p->cfg.n_fft, p->cfg.hop, p->cfg.n_mels);
   cacfe::FrontendArgs a;
   int launches = 1;
   a.norm = nullptr;
