@@ -24,9 +24,16 @@ under ``tests/golden/``):
     window arithmetic of ``load_samples``;
   * ``tfpcen.py``, and the feature functions of ``tfdataset.py`` / ``badwinner2.py``
     are executed from their own source over a numpy stand-in for the ``tf`` namespace,
-    which pins operation order and constants at the Python level.
-The TensorFlow/librosa *internals* (framing, window, FFT, scan) remain restated from
-documentation: for those, parity is UNPINNED and says so in DESIGN.md.
+    which pins operation order and constants at the Python level;
+  * round 2: ``audiodataset.load_data`` (gen_load_data_golden.py), ``predict_utils.load_samples``
+    with its Butterworth pre-filter (gen_filter_golden.py), ``identifytracks.signal_noise``
+    (gen_signal_golden.py) and the two model builders ``badwinner2.build_model`` /
+    ``wr_resnet_bird.WRResNet`` over an eager numpy Keras stand-in (gen_consumer_golden.py)
+    are executed from their own source in the same way.
+The TensorFlow / librosa / Keras *internals* (framing, window, FFT, scan, layer semantics)
+remain restated from documentation: for those, parity is UNPINNED and says so in DESIGN.md.
+(``tf.signal.hann_window`` is evaluated in float32 by TensorFlow; this module's float64
+window is the exact one, the stand-in's is TensorFlow's -- DESIGN.md section 4.)
 
 Two arithmetic modes:
   dtype=np.float64 : ground truth the CUDA path is compared against with the north-star
