@@ -17,8 +17,6 @@ Anything else (compression filters, variable-length strings, dense link storage,
 """
 from __future__ import annotations
 
-import struct
-
 import numpy as np
 
 SIGNATURE = b"\x89HDF\r\n\x1a\n"
@@ -89,7 +87,6 @@ class File:
         if ver in (0, 1):
             self.O, self.L = self.buf[pos + 13], self.buf[pos + 14]
             p = pos + 24 + (4 if ver == 1 else 0)
-            self.base = 0
             self.base = self._u(p, self.O)            # base address: every other address is relative to it
             p += 4 * self.O                            # base, free-space, end-of-file, driver-info
             # root group symbol table entry: link name offset, object header address, cache type, reserved, scratch
@@ -97,16 +94,12 @@ class File:
         elif ver in (2, 3):
             self.O, self.L = self.buf[pos + 9], self.buf[pos + 10]
             p = pos + 12
-            self.base = 0
             self.base = self._u(p, self.O)
             self.root_addr = self._addr(p + 3 * self.O)
         else:
             raise H5Unsupported(f"superblock version {ver}")
         if self.O not in (4, 8) or self.L not in (4, 8):
             raise H5Unsupported(f"offset / length sizes {self.O} / {self.L}")
-        if self.base == 0 and self.sb_pos != 0 and ver in (0, 1):
-            # files with a user block written by some tools keep base address 0 and absolute addresses: nothing to do
-            pass
 
     # ---- object headers ------------------------------------------------------------------------------------------------
     def _object(self, addr):
@@ -297,12 +290,11 @@ class File:
         if sig == b"TREE":
             if self.buf[addr + 4] != 0:
                 raise H5Error("expected a group B-tree node")
-            level, used = self.buf[addr + 5], self._u(addr + 6, 2)
+            used = self._u(addr + 6, 2)                 # (the node level does not matter: children are TREE or SNOD nodes)
             p = addr + 8 + 2 * self.O                   # past the sibling pointers
             for i in range(used):
                 child = self._addr(p + self.L + i * (self.L + self.O))
                 self._group_node(child, heap_data, out)
-            _ = level
         elif sig == b"SNOD":
             n = self._u(addr + 6, 2)
             esize = 2 * self.O + 24
