@@ -78,8 +78,9 @@ class MelAxisNorm(nn.Module):
 
 
 class BadWinner2(nn.Module):
-    def __init__(self, input_shape, num_labels, multi_label=False, add_dense=True, big_condense=True):
+    def __init__(self, input_shape, num_labels, multi_label=False, add_dense=True, big_condense=True, lme=False):
         super().__init__()
+        self.lme = lme
         n_mels, _, c_in = input_shape
         if big_condense and n_mels not in (160, 96):
             raise ValueError(f"Unhandle mel channels {n_mels}")       # badwinner2.py:263
@@ -116,17 +117,17 @@ class BadWinner2(nn.Module):
         x = self.features(x.permute(0, 3, 1, 2))
         if self.head is None:
             return x.permute(0, 2, 3, 1)
-        x = F.leaky_relu(self.head(x), 0.01).mean(dim=(2, 3))          # GlobalAveragePooling2D
+        x = F.leaky_relu(self.head(x), 0.01)
+        if self.lme:   # LMELayer(axis=1, sharpness=5) then (axis=2), keepdims (badwinner2.py:303-305, 343-355): NHWC axes 1, 2 = H, W
+            x = _logmeanexp(_logmeanexp(x, 2, keepdim=True), 3, keepdim=True)
+        x = x.mean(dim=(2, 3))                                         # GlobalAveragePooling2D
         return torch.sigmoid(x) if self.multi_label else torch.softmax(x, dim=-1)
 
 
 def build_model(input_shape, norm_layer, num_labels, multi_label=False, lme=False, add_dense=True, big_condense=True,
                 input_name="input"):
-    """badwinner2.build_model's signature (badwinner2.py:212-222).  `norm_layer` is unused there too; `lme=True` (off in
-    every caller) is not restated."""
-    if lme:
-        raise NotImplementedError("LMELayer head (badwinner2.py:303-305) is off in every reference caller")
-    return BadWinner2(tuple(input_shape), num_labels, multi_label, add_dense, big_condense)
+    """badwinner2.build_model's signature (badwinner2.py:212-222).  `norm_layer` is unused there too."""
+    return BadWinner2(tuple(input_shape), num_labels, multi_label, add_dense, big_condense, lme)
 
 
 # ------------------------------------------------------------------------------------------------ wr_resnet_bird
@@ -163,8 +164,8 @@ class _BasicBlock(nn.Module):
         return F.relu(x) if self.relu_out else x
 
 
-def _logmeanexp(x, dim, sharpness=5.0):
-    return (torch.logsumexp(x * sharpness, dim=dim) - math.log(x.shape[dim])) / sharpness
+def _logmeanexp(x, dim, sharpness=5.0, keepdim=False):
+    return (torch.logsumexp(x * sharpness, dim=dim, keepdim=keepdim) - math.log(x.shape[dim])) / sharpness
 
 
 class WRResNetBird(nn.Module):

@@ -31,6 +31,7 @@ CASES = {
     "badwinner2_96_sig": ("badwinner2.py", "build_model", (96, 257, 1), lambda shp: (shp, None, 5), {"multi_label": True}, "power"),
     "badwinner2_160_small": ("badwinner2.py", "build_model", (160, 200, 3), lambda shp: (shp, None, 4), {"big_condense": False}, "power"),
     "badwinner2_nodense": ("badwinner2.py", "build_model", (96, 140, 1), lambda shp: (shp, None, 3), {"add_dense": False}, "power"),
+    "badwinner2_lme": ("badwinner2.py", "build_model", (96, 200, 1), lambda shp: (shp, None, 6), {"lme": True, "multi_label": True}, "power"),
     "wr_resnet_120": ("resnet/wr_resnet_bird.py", "WRResNet", (120, 512, 1), lambda shp: (shp, 6), {}, "signed"),
     "wr_resnet_160_k2": ("resnet/wr_resnet_bird.py", "WRResNet", (160, 256, 3), lambda shp: (shp, 9), {"depth": 16, "k": 2}, "signed"),
 }
@@ -50,7 +51,7 @@ def main():
         kn.reset(seed)
         tf, tfp = kn.make_tf(x)
         ns = {"tf": tf, "tfp": tfp, "logging": logging}
-        names = ["build_model", "MagTransform"] if fn == "build_model" else ["WRResNet", "logmeanexp", "wr_block", "basic_block"]
+        names = ["build_model", "MagTransform", "LMELayer"] if fn == "build_model" else ["WRResNet", "logmeanexp", "wr_block", "basic_block"]
         gg.cut_out(os.path.join(gg.REF, path), names, ns)
         with contextlib.redirect_stdout(io.StringIO()):
             model = ns[fn](*args(shape), **kwargs)

@@ -85,7 +85,7 @@ def _golden_cases():
         return json.load(fh)
 
 
-@pytest.mark.parametrize("tag", ["badwinner2_160", "badwinner2_96_sig", "badwinner2_160_small", "badwinner2_nodense",
+@pytest.mark.parametrize("tag", ["badwinner2_160", "badwinner2_96_sig", "badwinner2_160_small", "badwinner2_nodense", "badwinner2_lme",
                                  "wr_resnet_120", "wr_resnet_160_k2"])
 def test_consumers_match_the_executed_reference_graph(tag):
     """The reference's build_model / WRResNet, run as they are over the numpy Keras stand-in with seeded variables, against
