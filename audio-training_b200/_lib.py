@@ -29,7 +29,7 @@ FRAME_TF_PAD_END, FRAME_CENTER_ZERO, FRAME_CENTER_REFLECT, FRAME_NO_PAD = 0, 1, 
 LAYOUT_BMTC, LAYOUT_BTM = 0, 1
 MEL_BANDED_FP32, MEL_TC_3XTF32 = 0, 1
 NORM_TENSOR, NORM_CLIP, NORM_NONE = 0, 1, 2
-COMPRESS_MAG_POW, COMPRESS_POWER_TO_DB, COMPRESS_MINMAX, COMPRESS_STD = 0, 1, 2, 3
+COMPRESS_MAG_POW, COMPRESS_POWER_TO_DB, COMPRESS_MINMAX, COMPRESS_STD, COMPRESS_MEAN_SUB = 0, 1, 2, 3, 4
 STATUS_NAMES = {0: "CACFE_OK", -1: "CACFE_EINVAL", -2: "CACFE_ESHAPE", -3: "CACFE_EDTYPE", -4: "CACFE_EDEVICE",
                 -5: "CACFE_EALIGN", -6: "CACFE_ECUDA", -7: "CACFE_ENOMEM"}
 
@@ -79,6 +79,7 @@ PROTOTYPES = {
     "cacfe_mix_up": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "cacfe_mel_from_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cacfe_ema": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "cacfe_ema_init": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),
     "cacfe_pcen": (c_int, [c_void_p, POINTER(PcenParams), c_void_p, c_void_p, c_int, c_longlong, c_int, c_int,
                            c_void_p, c_void_p]),
     "cacfe_compress": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p,

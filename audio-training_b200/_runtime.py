@@ -20,7 +20,7 @@ _FRAMING = {"tf_pad_end": _lib.FRAME_TF_PAD_END, "center_zero": _lib.FRAME_CENTE
 _LAYOUT = {"bmtc": _lib.LAYOUT_BMTC, "btm": _lib.LAYOUT_BTM}
 _SCOPE = {"tensor": _lib.NORM_TENSOR, "clip": _lib.NORM_CLIP, "none": _lib.NORM_NONE}
 _COMPRESS = {"mag_pow": _lib.COMPRESS_MAG_POW, "power_to_db": _lib.COMPRESS_POWER_TO_DB,
-             "minmax": _lib.COMPRESS_MINMAX, "std": _lib.COMPRESS_STD}
+             "minmax": _lib.COMPRESS_MINMAX, "std": _lib.COMPRESS_STD, "mean_sub": _lib.COMPRESS_MEAN_SUB}
 
 
 @dataclass(frozen=True)
@@ -281,14 +281,24 @@ class Plan:
             self._handle, _ptr(spec[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, T, _stream(self.device))))
         return out
 
-    def ema(self, x, smooth, time_axis=1):
+    def ema(self, x, smooth, time_axis=1, initial_state=None):
+        """tfpcen.ExponentialMovingAverage.call: initial_state = tf.scan's initializer (x with the time axis removed);
+        None = inputs[:, 0, :], what PCEN.call passes (tfpcen.py:92)."""
         x = self._check_in(x, "ema")
         B, opc, T, inner = _split_axes(x, time_axis)
         out = torch.empty_like(x)
+        init = None
+        if initial_state is not None:
+            init = self._check_in(initial_state, "ema initial_state")
+            want = tuple(x.shape[:time_axis]) + tuple(x.shape[time_axis + 1:])
+            if tuple(init.shape) != want:
+                raise ValueError(f"ema: initial_state must have shape {want}, got {tuple(init.shape)}")
+            init = init.reshape(B, -1)
         if x.numel() == 0:
             return out
-        self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_ema(
-            self._handle, float(smooth), _ptr(x[b0:b0 + nb]), _ptr(out[b0:b0 + nb]), nb, opc, T, inner, _stream(self.device))))
+        self._batched(B, lambda b0, nb: _lib.check(self._lib.cacfe_ema_init(
+            self._handle, float(smooth), _ptr(x[b0:b0 + nb]), _ptr(init[b0:b0 + nb]) if init is not None else None,
+            _ptr(out[b0:b0 + nb]), nb, opc, T, inner, _stream(self.device))))
         return out
 
     def pcen(self, x, params=None, time_axis=1):
@@ -372,16 +382,25 @@ class Plan:
                                           _stream(self.device)))
         return out
 
-    def compress(self, x, mode, param=0.0, per_clip=False):
+    def compress(self, x, mode, param=0.0, per_clip=False, row_len=None):
+        """Statistic scope: the whole tensor, one entry per clip (per_clip), or one entry per contiguous run of row_len
+        elements (mean_sub: one mel row of a [.., n_mels, T, C] image)."""
         x = self._check_in(x, "compress")
-        entries = x.shape[0] if per_clip else 1
-        per_entry = x.numel() // entries
         out = torch.empty_like(x)
         if x.numel() == 0:
             return out
-        ws = self.workspace(self._lib.cacfe_compress_workspace_bytes(entries, per_entry))
-        _lib.check(self._lib.cacfe_compress(self._handle, _COMPRESS[mode], float(param), _ptr(x), _ptr(out), entries,
-                                            per_entry, _ptr(ws), _stream(self.device)))
+        if row_len is not None:
+            if x.numel() % int(row_len):
+                raise ValueError("compress: row_len does not divide the tensor")
+            entries, per_entry = x.numel() // int(row_len), int(row_len)
+        else:
+            entries = x.shape[0] if per_clip else 1
+            per_entry = x.numel() // entries
+        xf, of = x.view(entries, per_entry), out.view(entries, per_entry)
+        ws = self.workspace(self._lib.cacfe_compress_workspace_bytes(min(entries, self.MAX_BATCH), per_entry))
+        self._batched(entries, lambda e0, ne: _lib.check(self._lib.cacfe_compress(
+            self._handle, _COMPRESS[mode], float(param), _ptr(xf[e0:e0 + ne]), _ptr(of[e0:e0 + ne]), ne, per_entry, _ptr(ws),
+            _stream(self.device))))
         return out
 
 

@@ -908,8 +908,8 @@ int cacfe_mel_from_spectrogram(cacfe_plan* p, const float* spec, float* feat, in
   return check_launch(p, "mel_from_spectrogram");
 }
 
-int cacfe_ema(cacfe_plan* p, float smooth, const float* in, float* out, int B, long long outer_per_clip, int T, int inner,
-              void* stream) {
+int cacfe_ema_init(cacfe_plan* p, float smooth, const float* in, const float* init, float* out, int B, long long outer_per_clip,
+                   int T, int inner, void* stream) {
   if (!p || !in || !out) return fail(CACFE_EINVAL, "ema: null argument");
   if (in == out) return fail(CACFE_EINVAL, "ema: in-place operation is not supported");
   if (B < 1 || B > 65535 || T < 1 || inner < 1 || outer_per_clip < 1) return fail(CACFE_ESHAPE, "ema: bad shape");
@@ -917,6 +917,7 @@ int cacfe_ema(cacfe_plan* p, float smooth, const float* in, float* out, int B, l
   cacfe::PcenArgs a{};
   a.in = in;
   a.out = out;
+  a.init = init;
   a.T = T;
   a.inner = inner;
   a.rows_per_clip = (int)(outer_per_clip * inner);
@@ -925,6 +926,11 @@ int cacfe_ema(cacfe_plan* p, float smooth, const float* in, float* out, int B, l
   const PcenGrid g = pcen_grid(a.rows_per_clip);
   cacfe::ema_kernel<<<dim3(g.gx, B), g.block, 0, (cudaStream_t)stream>>>(a);
   return check_launch(p, "ema");
+}
+
+int cacfe_ema(cacfe_plan* p, float smooth, const float* in, float* out, int B, long long outer_per_clip, int T, int inner,
+              void* stream) {
+  return cacfe_ema_init(p, smooth, in, nullptr, out, B, outer_per_clip, T, inner, stream);
 }
 
 static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* in, float* out, int B,
@@ -1192,7 +1198,7 @@ int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float*
   if (!p || !in || !out) return fail(CACFE_EINVAL, "compress: null argument");
   if (in == out) return fail(CACFE_EINVAL, "compress: in-place operation is not supported");
   if (entries < 1 || entries > 65535 || per_entry < 1) return fail(CACFE_ESHAPE, "compress: bad shape");
-  if (mode < 0 || mode > 3) return fail(CACFE_EINVAL, "compress: unknown mode %d", mode);
+  if (mode < 0 || mode > 4) return fail(CACFE_EINVAL, "compress: unknown mode %d", mode);
   CUDA_TRY(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = compress_blocks(entries, per_entry);
@@ -1216,6 +1222,9 @@ int cacfe_compress(cacfe_plan* p, int mode, float param, const float* in, float*
       break;
     case CACFE_COMPRESS_MINMAX:
       cacfe::compress_kernel<cacfe::COMPRESS_MINMAX><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
+      break;
+    case CACFE_COMPRESS_MEAN_SUB:
+      cacfe::compress_kernel<cacfe::COMPRESS_MEAN_SUB><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);
       break;
     default:
       cacfe::compress_kernel<cacfe::COMPRESS_STD><<<grid, 256, 0, st>>>(in, out, per_entry, param, stats);

@@ -4,6 +4,7 @@
 //   POWER_TO_DB  power_to_db       tfdataset.py:1906-1913 (== librosa.power_to_db(ref=np.max), predict_utils.py:216)
 //   STD          normalize_std     tfdataset.py:1883-1893                        (x-mean)/(std + 1e-7)
 //   MAG_POW      MagTransform      badwinner2.py:32-49                           x ** sigmoid(a)   (no statistic)
+//   MEAN_SUB     get_spect(mean_sub=True)  predict_utils.py:233-236              x - mean   (one entry per mel row)
 //
 // The tensor is a flat run of `per_entry` floats per scope entry (1 entry = whole tensor, or B = per clip).
 // Pass 1 (stats_kernel) writes block partials, stats_finalize_kernel folds them, pass 2 applies.  HBM bound.
@@ -12,7 +13,7 @@
 
 namespace cacfe {
 
-enum : int { COMPRESS_MAG_POW = 0, COMPRESS_POWER_TO_DB = 1, COMPRESS_MINMAX = 2, COMPRESS_STD = 3 };
+enum : int { COMPRESS_MAG_POW = 0, COMPRESS_POWER_TO_DB = 1, COMPRESS_MINMAX = 2, COMPRESS_STD = 3, COMPRESS_MEAN_SUB = 4 };
 
 struct Stats {  // one per scope entry
   float mn, mx;
@@ -120,6 +121,8 @@ __global__ void __launch_bounds__(256) compress_kernel(const float* __restrict__
     const double var = fmax(st.sumsq / (double)per_entry - mean * mean, 0.0);
     c0 = (float)mean;
     c1 = (float)sqrt(var) + 1e-7f;  // keras.backend.epsilon()
+  } else if (MODE == COMPRESS_MEAN_SUB) {
+    c0 = (float)(stats[blockIdx.y].sum / (double)per_entry);   // the correctly rounded f32 mean (tf.reduce_mean sums in f32)
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256) compress_kernel(const float* __restrict__
     if (MODE == COMPRESS_MAG_POW) return exp2f(param * log2f(v));  // v ** param for v >= 0 (0 -> 0, like tf.pow)
     if (MODE == COMPRESS_POWER_TO_DB) return fmaxf(10.0f * log10f(fmaxf(1e-10f, v)) - c0, -80.0f);
     if (MODE == COMPRESS_MINMAX) return 2.0f * ((v - c0) / c1) - 1.0f;
+    if (MODE == COMPRESS_MEAN_SUB) return v - c0;
     return (v - c0) / c1;
   };
   if ((per_entry & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {

@@ -31,6 +31,7 @@ struct PcenArgs {
   float2* partial;               // [B][gridDim.x]           (REDUCE)
   const float2* extremes;        // [1] or [B] (min, max)    (APPLY)
   int per_clip_extremes;
+  const float* init;             // ema_kernel: initial state [outer][inner], or nullptr = inputs[:, 0, :]
 };
 
 enum : int { PCEN_REDUCE = 0, PCEN_APPLY = 1, PCEN_RAW = 2 };
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(256) ema_kernel(const PcenArgs a) {
   const size_t base = ((size_t)clip * (a.rows_per_clip / a.inner) + o) * a.T * a.inner + i;
   const float* x = a.in + base;
   float* y = a.out + base;
-  float m = x[0];
+  // tf.scan's initializer (tfpcen.py:36-38): any state; the reference's only caller passes inputs[:, 0, :] (tfpcen.py:92)
+  float m = a.init != nullptr ? a.init[((size_t)clip * (a.rows_per_clip / a.inner) + o) * a.inner + i] : x[0];
   int t = 0;
   float v[kEmaUnroll], nv[kEmaUnroll];
   if (a.T >= kEmaUnroll) {

@@ -91,8 +91,9 @@ def make_layers(tf):
 
         def call(self, inputs, initial_state=None):
             w = _scalar(self._weights_var)
-            # the reference's only use passes initial_state = inputs[:, 0, :] (tfpcen.py:92), which is what the kernel assumes
-            return wrap(lambda x: plan_for(x).ema(x.contiguous(), w, 1), [inputs])
+            if initial_state is None:   # the reference's only use passes inputs[:, 0, :] (tfpcen.py:92): the kernel's default
+                return wrap(lambda x: plan_for(x).ema(x.contiguous(), w, 1), [inputs])
+            return wrap(lambda x, s0: plan_for(x).ema(x.contiguous(), w, 1, initial_state=s0.contiguous()), [inputs, initial_state])
 
         def get_config(self):
             return {"coeff_init": self._coeff_init, "trainable": self._trainable}

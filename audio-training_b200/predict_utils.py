@@ -45,9 +45,9 @@ def get_spect(data, sr, hop_length, mean_sub, use_mfcc, mel_break, htk, n_mels, 
     """predict_utils.py:163-239, default branch (htk=True): |librosa.stft(data, n_fft, hop)| ** power -> custom mel ->
     [n_mels, T, channels].  `data` may also be a batch [W, N] -> [W, n_mels, T, channels].
     `pad_mode`: librosa >= 0.10 pads with zeros ("constant"), older releases reflect; the version is un-pinned."""
-    if not htk or use_mfcc or mean_sub:
-        raise NotImplementedError("get_spect: htk=False / use_mfcc / mean_sub are off in every reference caller "
-                                  "(predict_utils.py:17,19,26) and are not built")
+    if not htk or use_mfcc:
+        raise NotImplementedError("get_spect: htk=False / use_mfcc are off in every reference caller "
+                                  "(predict_utils.py:17,19) and are not built")
     t, restore = rt.to_device(data)
     single = t.dim() == 1
     if single:
@@ -57,6 +57,8 @@ def get_spect(data, sr, hop_length, mean_sub, use_mfcc, mel_break, htk, n_mels, 
     out = plan.frontend(t)
     if db_scale:  # librosa.power_to_db(mel, ref=np.max) per window (predict_utils.py:216-217)
         out = plan.compress(out, "power_to_db", per_clip=True)
+    if mean_sub:  # mel - reduce_mean(mel, axis=1): every mel row loses its mean over time (predict_utils.py:233-236); the
+        out = plan.compress(out, "mean_sub", row_len=out.shape[-2] * out.shape[-1])   # channel repeat that follows copies rows
     return restore(out[0] if single else out)
 
 
@@ -124,8 +126,8 @@ def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=281,
     [fmin, fmax]).  One batched GPU launch for every window of every track."""
     logging.info("Loading samples with length %s stride %s hop length %s n mels %s fmin %s fmax %s n_fft %s",
                  segment_length, stride, hop_length, n_mels, fmin, fmax, n_fft)
-    if not htk or use_mfcc or mean_sub:
-        raise NotImplementedError("load_samples: htk=False / use_mfcc / mean_sub are not built")
+    if not htk or use_mfcc:
+        raise NotImplementedError("load_samples: htk=False / use_mfcc are not built")
     frames = np.asarray(frames)
     size = int(sr * segment_length)
     segments = []
@@ -160,6 +162,8 @@ def load_samples(frames, sr, tracks, segment_length=3, stride=1, hop_length=281,
     feats = plan.frontend(dev)
     if db_scale:
         feats = plan.compress(feats, "power_to_db", per_clip=True)
+    if mean_sub:
+        feats = plan.compress(feats, "mean_sub", row_len=feats.shape[-2] * feats.shape[-1])
     if as_numpy:
         feats = feats.cpu().numpy()
     out, i = [], 0

@@ -17,7 +17,8 @@ def _plan(device):
 
 class ExponentialMovingAverage:
     """tfpcen.py:8-39.  call(inputs[batch, seq, filters], initial_state): M[t] = w x[t] + (1-w) M[t-1] with
-    w = clip(smooth, 0, 1).  As at the reference's only call site (tfpcen.py:92) the initial state is inputs[:, 0, :]."""
+    w = clip(smooth, 0, 1), M[-1] = initial_state (tf.scan's initializer); None = inputs[:, 0, :], what the reference's only
+    call site passes (tfpcen.py:92)."""
 
     def __init__(self, coeff_init, trainable=False):
         self.name = "EMA"
@@ -31,12 +32,10 @@ class ExponentialMovingAverage:
 
     def call(self, inputs, initial_state=None, time_axis=1):
         t, restore = rt.to_device(inputs)
-        if initial_state is not None:
+        first = None
+        if initial_state is not None:   # tf.scan's initializer; PCEN.call passes inputs[:, 0, :] (tfpcen.py:92)
             first, _ = rt.to_device(initial_state)
-            if not bool((first == t.select(time_axis, 0)).all()):
-                raise NotImplementedError("ExponentialMovingAverage: only initial_state = inputs[:, 0] is built "
-                                          "(the reference's only use, tfpcen.py:92)")
-        return restore(_plan(t.device.index).ema(t, float(self._weights[0]), time_axis))
+        return restore(_plan(t.device.index).ema(t, float(self._weights[0]), time_axis, initial_state=first))
 
     __call__ = call
 

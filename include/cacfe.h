@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CACFE_VERSION 102 /* 0.1.2: + cacfe_stft_stats */
+#define CACFE_VERSION 103 /* 0.1.3: + cacfe_ema_init, CACFE_COMPRESS_MEAN_SUB */
 
 typedef enum cacfe_status {
   CACFE_OK = 0,
@@ -96,7 +96,8 @@ typedef enum cacfe_compress_mode {
   CACFE_COMPRESS_MAG_POW = 0,     /* badwinner2.MagTransform: x ** param, param = sigmoid(a) (badwinner2.py:47-49) */
   CACFE_COMPRESS_POWER_TO_DB = 1, /* tfdataset.power_to_db (tfdataset.py:1906-1913) */
   CACFE_COMPRESS_MINMAX = 2,      /* normalize_minmax (tfpcen.py:105-110, tfdataset.py:1897-1902) */
-  CACFE_COMPRESS_STD = 3          /* normalize_std (tfdataset.py:1883-1893) */
+  CACFE_COMPRESS_STD = 3,         /* normalize_std (tfdataset.py:1883-1893) */
+  CACFE_COMPRESS_MEAN_SUB = 4     /* get_spect(mean_sub=True): x - mean over each entry = one mel row (predict_utils.py:233-236) */
 } cacfe_compress_mode;
 
 typedef struct cacfe_plan cacfe_plan;
@@ -161,6 +162,10 @@ int cacfe_mel_from_spectrogram(cacfe_plan* plan, const float* spec_dev, float* f
 /* ---- a10: ExponentialMovingAverage.call tfpcen.py:33-39 on x[outer][T][inner], recurrence along T. */
 int cacfe_ema(cacfe_plan* plan, float smooth, const float* in_dev, float* out_dev, int B, long long outer_per_clip,
               int T, int inner, void* stream);
+/* the same with tf.scan's initializer (tfpcen.py:33-38) given explicitly: init_dev [B * outer_per_clip][inner], the state
+ * before the first step; NULL = inputs[:, 0, :], what PCEN.call passes (tfpcen.py:92). */
+int cacfe_ema_init(cacfe_plan* plan, float smooth, const float* in_dev, const float* init_dev, float* out_dev, int B,
+                   long long outer_per_clip, int T, int inner, void* stream);
 
 /* ---- a10-a12: PCEN.call tfpcen.py:89-99 on x[B * outer_per_clip][T][inner].
  * [B,T,F] (the reference contract): outer_per_clip = 1, inner = F.  in_dev != out_dev. */

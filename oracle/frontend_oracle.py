@@ -283,15 +283,17 @@ def mel_spec(stft, sr, n_fft, hop_length, n_mels, fmin, fmax, break_freq=1750, p
 
 def get_spect(data, sr=SR, hop_length=HOP, mel_break=BREAK_FREQ, n_mels=N_MELS, fmin=FMIN,
               fmax=FMAX, n_fft=N_FFT, power=2, db_scale=False, channels=1,
-              pad_mode="constant", dtype=np.float64):
+              pad_mode="constant", dtype=np.float64, mean_sub=False):
     """Path B, default branch htk=True of predict_utils.py:163-239 (:190-215).  Q9: the fmax
-    argument is `11000 if fmin is None else fmax`."""
+    argument is `11000 if fmin is None else fmax`.  mean_sub (:233-236): every mel row minus its mean over time."""
     spec = np.abs(stft_librosa(data, n_fft, hop_length, pad_mode, dtype))
     mel = mel_spec(spec, sr, n_fft, hop_length, n_mels, 100 if fmin is None else fmin,
                    11000 if fmin is None else fmax, mel_break, power, dtype)
     if db_scale:
         mel = librosa_power_to_db(mel)
     mel = mel[..., None]
+    if mean_sub:
+        mel = mel - np.mean(mel, axis=1, keepdims=True)
     if channels > 1:
         mel = np.repeat(mel, channels, axis=2)
     return mel
@@ -311,14 +313,15 @@ def mel_from_spectrogram(spec, weights=None, power=1, dtype=np.float64):
 # --------------------------------------------------------------------------------------
 # a10-a12  PCEN                                                      tfpcen.py:8-110
 # --------------------------------------------------------------------------------------
-def ema(x, smooth=0.04, dtype=np.float64, axis=1):
-    """tfpcen.py:8-39: w = clip(smooth,0,1); M[t] = w*x[t] + (1-w)*M[t-1], M[-1] := x[:,0]
-    (tfpcen.py:92), scanned sequentially along `axis` (reference: axis 1 of [B,T,F])."""
+def ema(x, smooth=0.04, dtype=np.float64, axis=1, initial_state=None):
+    """tfpcen.py:8-39: w = clip(smooth,0,1); M[t] = w*x[t] + (1-w)*M[t-1], scanned sequentially along `axis`
+    (reference: axis 1 of [B,T,F]).  M[-1] = initial_state (tf.scan's initializer, tfpcen.py:36-38); None = x[:,0],
+    what PCEN.call passes (tfpcen.py:92)."""
     x = np.moveaxis(np.asarray(x, dtype=dtype), axis, 0)
     w = dtype(min(max(smooth, 0.0), 1.0))
     one_m_w = dtype(1.0) - w
     out = np.empty_like(x)
-    acc = x[0]
+    acc = x[0] if initial_state is None else np.asarray(initial_state, dtype=dtype)
     for t in range(x.shape[0]):
         acc = w * x[t] + one_m_w * acc
         out[t] = acc

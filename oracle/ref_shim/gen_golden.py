@@ -155,6 +155,9 @@ def main():
         np.asarray(predict_utils.get_spect(clips_norm[i], 48000, 281, False, False, 1000, True, 160,
                                            100, 11000, 4096, 2, False)) for i in range(2)])
     assert spect_b.shape == (2, 160, 513, 1)
+    spect_b_ms = np.asarray(predict_utils.get_spect(clips_norm[0], 48000, 281, True, False, 1000, True, 160,
+                                                    100, 11000, 4096, 2, False, channels=3))   # mean_sub=True, then x3
+    assert spect_b_ms.shape == (160, 513, 3)
 
     # ---------------- path C: stored magnitude spectrogram -> mel (tfdataset.py:1082-1090) --
     mag = np.abs(_librosa_stft(clips_norm[0], n_fft=4096, hop_length=281))  # what audiowriter stores
@@ -176,6 +179,10 @@ def main():
     layer2.ema._weights[:] = 0.25
     pcen_small2 = layer2(small_btf)
     minmax_small = tfpcen.normalize_minmax(small_btf)
+    # ExponentialMovingAverage.call with an initial state other than inputs[:, 0, :] (tfpcen.py:33-39); own generator so that
+    # the draws above keep their values
+    ema_state = (np.random.default_rng(77).random((2, 8)).astype(np.float32) * 2.0 - 0.5)
+    ema_init_out = tfpcen.ExponentialMovingAverage(0.3)(small_btf, initial_state=ema_state)
 
     # ---------------- a13/a14 ---------------------------------------------------------------
     mel1 = img_a[0, :, :, 0]
@@ -193,9 +200,9 @@ def main():
         small=small, norm_np=norm_np, norm_tf=norm_tf, const_clip=const_clip,
         clips_norm_head=clips_norm[:, :64],
         path_a=img_a[..., 0], path_a_channels=np.asarray([3]),
-        path_b=spect_b[..., 0], path_c=mel_c[..., 0],
+        path_b=spect_b[..., 0], path_c=mel_c[..., 0], path_b_mean_sub=spect_b_ms[..., 0],
         pcen=pcen_out, ema=ema_out, small_btf=small_btf, pcen_small=pcen_small,
-        pcen_small2=pcen_small2, minmax_small=minmax_small,
+        pcen_small2=pcen_small2, minmax_small=minmax_small, ema_state=ema_state, ema_init_out=ema_init_out,
         power_to_db=db, normalize_std=std, normalize_minmax=mm2, mag_transform=magt,
         pcen_weight_names=np.asarray(weight_names),
         pcen_weight_values=np.asarray([float(v[0]) for _, v in tfpcen.PCEN()._added]

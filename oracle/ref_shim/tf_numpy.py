@@ -115,6 +115,11 @@ def repeat(x, repeats, axis=None, name=None):
     return np.repeat(np.asarray(x), repeats, axis=axis)
 
 
+def reduce_mean(x, axis=None, keepdims=False, name=None):
+    x = np.asarray(x)
+    return np.mean(x, axis=axis, keepdims=keepdims, dtype=x.dtype)   # TF keeps the input dtype (numpy: pairwise f32 sum)
+
+
 def constant(value, dtype=None, name=None):
     return np.asarray(value) if dtype is None else np.asarray(value, dtype=dtype)
 

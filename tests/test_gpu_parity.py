@@ -327,6 +327,16 @@ def test_path_b(oracle, golden, xn, pad_mode):
     assert got3.shape == (160, 513, 3)
     db = atb.get_spect(xn[0], 48000, 281, False, False, 1000, True, 160, 100, 11000, 4096, 2, True)
     check(oracle, db, oracle.get_spect(xn[0], db_scale=True), 5.0, what="db_scale")
+    # mean_sub=True (predict_utils.py:233-236): every mel row minus its mean over time, then the channel repeat.  The budget
+    # of a difference is the budget of its two terms.
+    ms = atb.get_spect(xn[0], 48000, 281, True, False, 1000, True, 160, 100, 11000, 4096, 2, False, channels=3)
+    assert ms.shape == (160, 513, 3) and np.array_equal(ms[..., 0], ms[..., 2])
+    before = oracle.get_spect(xn[0])[..., 0]
+    tol = 1e-4 * (np.abs(before) + np.abs(before.mean(axis=1, keepdims=True))) + 1e-5
+    assert (np.abs(ms[..., 0] - oracle.get_spect(xn[0], mean_sub=True)[..., 0]) <= tol).all(), "mean_sub vs f64 oracle"
+    assert (np.abs(ms[..., 0] - golden["path_b_mean_sub"]) <= 2.0 * tol).all(), "mean_sub vs reference-code golden"
+    batch = atb.get_spect(xn[:2], 48000, 281, True, False, 1000, True, 160, 100, 11000, 4096, 2, False)
+    assert np.array_equal(batch[0, :, :, 0], ms[..., 0])   # rows are independent of the batch
 
 
 def test_load_samples(oracle):
@@ -625,6 +635,21 @@ def test_ema_bit_exact(oracle, golden):
     assert np.array_equal(got, oracle.ema(x, dtype=np.float32))
 
 
+def test_ema_initial_state(oracle, golden):
+    """ExponentialMovingAverage.call(inputs, initial_state) with a state that is not inputs[:, 0, :] (tfpcen.py:33-39): bit-exact
+    against the reference class executed over the stand-in, on the rank-3 contract and along another axis."""
+    s, st = golden["small_btf"], golden["ema_state"]
+    got = atb.ExponentialMovingAverage(0.3)(s, initial_state=st)
+    assert np.array_equal(got, golden["ema_init_out"])
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 5, 37, 2)).astype(np.float32)
+    s0 = rng.standard_normal((3, 5, 2)).astype(np.float32)
+    got = atb.ExponentialMovingAverage(0.11).call(x, initial_state=s0, time_axis=2)
+    assert np.array_equal(got, oracle.ema(x, 0.11, np.float32, axis=2, initial_state=s0))
+    with pytest.raises(ValueError):
+        atb.ExponentialMovingAverage(0.11).call(x, initial_state=s0[:, :4], time_axis=2)
+
+
 def test_pcen(oracle, golden):
     x = np.swapaxes(golden["path_a"], 1, 2).copy()
     layer = atb.PCEN()
@@ -908,6 +933,7 @@ def test_keras_layer_adapter(oracle, golden):
     check(oracle, got, golden["pcen"], 2.0, what="Keras-layer PCEN vs reference-code golden")
     assert np.array_equal(got, atb.PCEN()(x))
     assert np.array_equal(L.ExponentialMovingAverage(0.04, True)(x, initial_state=x[:, 0, :]), golden["ema"])
+    assert np.array_equal(L.ExponentialMovingAverage(0.3)(golden["small_btf"], initial_state=golden["ema_state"]), golden["ema_init_out"])
     l2 = L.PCEN()
     l2.gain[:], l2.root[:], l2.bias[:] = 1.3, 0.5, 1.5                           # clamps: gain <= 1, root >= 1
     l2.ema._weights_var[:] = 0.25

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libcacfe.so does not export {name}"
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert lib.cacfe_version() == 102
+    assert lib.cacfe_version() == 103
 
 
 def test_native_filterbank_matches_reference_goldens(golden_banks):

@@ -97,6 +97,11 @@ def test_path_b(oracle, golden, clips):
         assert got.shape == (160, 513, 1)
         _check(oracle, got[..., 0], golden["path_b"][i], 0.05)
         _check(oracle, golden["path_b"][i], oracle.get_spect(xn[i], dtype=np.float64)[..., 0])
+    # mean_sub=True (predict_utils.py:233-236), executed by the reference's own get_spect: rows lose their time mean
+    ms = oracle.get_spect(xn[0], dtype=np.float64, mean_sub=True)[..., 0]
+    before = oracle.get_spect(xn[0], dtype=np.float64)[..., 0]
+    tol = 1e-4 * (np.abs(before) + np.abs(before.mean(axis=1, keepdims=True))) + 1e-5
+    assert (np.abs(golden["path_b_mean_sub"] - ms) <= tol).all()
 
 
 def test_path_c(oracle, golden, clips):
@@ -110,6 +115,8 @@ def test_path_c(oracle, golden, clips):
 def test_pcen_golden(oracle, golden):
     x = np.swapaxes(golden["path_a"], 1, 2)
     assert np.array_equal(oracle.ema(x, dtype=np.float32), golden["ema"])
+    # tf.scan's initializer other than inputs[:, 0, :]: the reference class executed over the stand-in (gen_golden.py)
+    assert np.array_equal(oracle.ema(golden["small_btf"], 0.3, np.float32, initial_state=golden["ema_state"]), golden["ema_init_out"])
     _check(oracle, oracle.pcen(x, dtype=np.float32), golden["pcen"], 0.05)
     _check(oracle, golden["pcen"], oracle.pcen(x, dtype=np.float64))
     s = golden["small_btf"]
