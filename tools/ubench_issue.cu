@@ -20,10 +20,10 @@ __device__ __forceinline__ float lo(u64 v) { return __uint_as_float((unsigned)v)
 
 constexpr int CH = 16;
 enum { M_FADD, M_FADD2, M_FMUL2, M_FFMA_RRR, M_FFMA_IMM, M_FFMA2, M_FADD2_LDS, M_FADD2_ALU, M_FADD2_FADD, M_FFMA2_ALU, M_LDS, M_FADD_LDS,
-       M_FADD2_STS, M_ALU, M_FADD2_2ALU, M_COUNT };
+       M_FADD2_STS, M_ALU, M_FADD2_2ALU, M_FFMA2_UR, M_FFMA2_UR16, M_COUNT };
 const char* kNames[M_COUNT] = {"FADD r,r", "FADD2", "FMUL2", "FFMA r,r,r", "FFMA r,imm,r", "FFMA2 r,r,r", "FADD2 + LDS.32 (1:1)", "FADD2 + IADD (1:1)",
                                "FADD2 + FADD (1:1)", "FFMA2 + IADD (1:1)", "LDS.32 alone", "FADD + LDS.32 (1:1)", "FADD2 + STS.32 (1:1)", "IADD alone",
-                               "FADD2 + 2 ALU (1:2)"};
+                               "FADD2 + 2 ALU (1:2)", "FFMA2 r,const,r (1 const)", "FFMA2 r,const,r (16 const)"};
 
 template <int MODE>
 __global__ void __launch_bounds__(384, 1) k(float* out, int iters, float seed) {
@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(384, 1) k(float* out, int iters, float seed) {
         if (MODE == M_FADD_LDS) { ADD1(s[c], s[c], sa[c]); acc += base[((c + 16 * r + it) & 255) * 32]; }
         if (MODE == M_FADD2_STS) { ADD2(v[c], v[c], a[c]); sm[((c + 16 * r) & 255) * 32 + threadIdx.x % 32 + 32 * (threadIdx.x / 32) * 0] = s[c]; }
         if (MODE == M_ALU) IADD(n[c], n[c], m[c]);
+        if (MODE == M_FFMA2_UR) FMA2(v[c], v[c], pk(0.999f, 1.001f), b[c]);                    // constant pair: a uniform-register operand
+        if (MODE == M_FFMA2_UR16) FMA2(v[c], v[c], pk(0.999f + 1e-3f * c, 1.001f - 1e-3f * c), b[c]);   // 16 different constant pairs
         if (MODE == M_FADD2_2ALU) { ADD2(v[c], v[c], a[c]); IADD(n[c], n[c], m[c]); LOPX(m[c], m[c], n[(c + 1) % CH]); }
       }
     }
@@ -105,6 +107,6 @@ void both() {
 int main() {
   both<M_FADD>(); both<M_FADD2>(); both<M_FMUL2>(); both<M_FFMA_RRR>(); both<M_FFMA_IMM>(); both<M_FFMA2>();
   both<M_ALU>(); both<M_LDS>(); both<M_FADD_LDS>(); both<M_FADD2_LDS>(); both<M_FADD2_STS>(); both<M_FADD2_ALU>(); both<M_FADD2_2ALU>();
-  both<M_FADD2_FADD>(); both<M_FFMA2_ALU>();
+  both<M_FADD2_FADD>(); both<M_FFMA2_ALU>(); both<M_FFMA2_UR>(); both<M_FFMA2_UR16>();
   return 0;
 }
