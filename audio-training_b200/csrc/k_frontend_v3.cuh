@@ -40,6 +40,9 @@ constexpr int kHalfStride = 68;                    // floats per half-exchange r
 constexpr int kHalfFloats = 64 * kHalfStride;      // 17408 B per group
 constexpr int kVThreads = kVGroups * 64;
 constexpr int kVTileFrames = 2 * kVGroups;
+#ifdef CACFE_K1_NORM_BATCH
+constexpr int kNormBatch = CACFE_K1_NORM_BATCH;
+#endif   // 16-byte groups loaded before the first is normalised and stored back
 constexpr int kNormIters = 6;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
 
 struct VSmem {
@@ -75,6 +78,27 @@ __device__ __forceinline__ void k1_jitter(unsigned salt) {
 __device__ __forceinline__ void k1_jitter(unsigned) {}
 #endif
 
+// Fast path of the tile normalisation (whole tile inside the clip): every thread takes up to kNormIters 16-byte groups, all loads
+// first.  A function of its own (A/B switch CACFE_K1_NORM_CALL): the register allocation of the FFT loop does not see it.
+__device__ __noinline__ void k1_normalise_full(float4* t4, int n4, int tid, float mn, float sc, float of) {
+  const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
+  float4 v[kNormIters];
+#pragma unroll
+  for (int u = 0; u < kNormIters; ++u) {
+    const int e = tid + u * kVThreads;
+    if (e < n4) v[u] = t4[e];
+  }
+#pragma unroll
+  for (int u = 0; u < kNormIters; ++u) {
+    const int e = tid + u * kVThreads;
+    if (e < n4) {
+      const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].x, v[u].y), mn2), sc2, of2);
+      const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].z, v[u].w), mn2), sc2, of2);
+      t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
+    }
+  }
+}
+
 // Mel job tables of the plan (mel_jobs.h), device copies.
 struct MelArgs {
   const float4* tw4;  // [32][64] stage twiddles, packed per output pair: (cos k, cos k+1, sin k, sin k+1)
@@ -84,16 +108,21 @@ struct MelArgs {
   int nq[kMelMaxSeg];
   int split_seg, total_quads;
   int spec_ratio, spec_bins;   // LAYOUT_SPEC: 4096 / n_fft and n_fft / 2 + 1
+  int tile_len, tile_pad;      // v3_smem_layout's tile geometry (read from the constant bank in the loop instead of re-derived)
 };
 
 // WINC: the Hann(4096) window is computed per thread by angle addition (two FFMA with immediates per value) instead of being
 // read from shared memory (one LDS.64 per two values): the kernel is shared-memory-wavefront bound, not FMA bound.  Shorter
 // transforms (zero-padded window) keep the table.
-template <int NQ, int LAYOUT, bool WINC = false>
+// HOT: the instantiation of the benchmarked path (per-clip normalisation on, no reflect padding, power 2) with those three run-time
+// switches resolved at compile time: the magnitude loop with its sqrt calls, the mirror pass and the un-normalised form leave
+// the code the twelve warps fetch.
+template <int NQ, int LAYOUT, bool WINC = false, bool HOT = false>
 __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const FrontendArgs a, const MelArgs mj,
                                                                       const int total_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
+  const bool has_norm = HOT || a.norm != nullptr, reflect = !HOT && a.reflect, magnitude = !HOT && a.power == 1;
   float4* s_tw4 = reinterpret_cast<float4*>(smem);   // [32 output pairs][64 n2]
   float2* s_win2 = reinterpret_cast<float2*>(smem + L.off_win);
   float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
@@ -139,9 +168,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const uint32_t bytes = (uint32_t)(c1 - c0) * 4u;
     const uint32_t bar = smem_u32(&s_full[s]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses vs the async write
-    mbar_expect_tx(bar, bytes + (a.norm != nullptr ? 16u : 0u));
+    mbar_expect_tx(bar, bytes + (has_norm ? 16u : 0u));
     bulk_g2s(smem_u32(s_tile + (size_t)s * L.tile_pad + (c0 - s_lo)), a.in + (size_t)b * a.n_samples + c0, bytes, bar);
-    if (a.norm != nullptr) bulk_g2s(smem_u32(s_nrm + 2 * s), a.norm + (b & ~1), 16u, bar);
+    if (has_norm) bulk_g2s(smem_u32(s_nrm + 2 * s), a.norm + (b & ~1), 16u, bar);
   };
 
   // Every warp normalises its slice of tile i in place (and writes the padding), then arrives on s_norm[i&1].
@@ -152,7 +181,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const uint32_t parity = (uint32_t)((i >> 1) & 1);
     mbar_wait_relaxed(smem_u32(&s_full[s]), parity);
     float mn = 0.0f, sc = 1.0f, of = 0.0f;
-    if (a.norm != nullptr) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
+    if (has_norm) {  // ((x - mn) / range + 1e-6 - 0.5) * 2, the reference's order with one rounding less
       const float2 nrm = s_nrm[2 * s + (b & 1)];
       mn = nrm.y;
       sc = 2.0f / nrm.x;      // range 0 -> inf -> (x - mn) * inf = NaN: constant clips give NaN features (Q1)
@@ -164,6 +193,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const int e_lo = s_lo < 0 ? (-s_lo) >> 2 : 0, e_hi = (a.n_samples - s_lo) >> 2;
     const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
     if (e_lo == 0 && e_hi >= n4) {  // the whole tile lies inside the clip (41 of 43 tiles): no padding to write
+#if defined(CACFE_K1_NORM_CALL)
+      k1_normalise_full(t4, n4, tid, mn, sc, of);
+#elif !defined(CACFE_K1_NORM_BATCH)   // load, normalise, store one 16-byte group at a time
 #pragma unroll
       for (int u = 0; u < kNormIters; ++u) {
         const int e = tid + u * kVThreads;
@@ -174,6 +206,28 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
         }
       }
+#else
+      // all loads first: the stores go through the same pointer, so the compiler will not move a later load above them, and
+      // every group would pay the shared-memory latency (the FFT registers are dead here: 24 registers are free)
+#pragma unroll
+      for (int u0 = 0; u0 < kNormIters; u0 += kNormBatch) {
+        float4 v[kNormBatch];
+#pragma unroll
+        for (int u = 0; u < kNormBatch; ++u) {
+          const int e = tid + (u0 + u) * kVThreads;
+          if (e < n4) v[u] = t4[e];
+        }
+#pragma unroll
+        for (int u = 0; u < kNormBatch; ++u) {
+          const int e = tid + (u0 + u) * kVThreads;
+          if (e < n4) {
+            const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].x, v[u].y), mn2), sc2, of2);
+            const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].z, v[u].w), mn2), sc2, of2);
+            t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
+          }
+        }
+      }
+#endif
     } else {
 #pragma unroll 1
       for (int e = tid; e < n4; e += kVThreads) {
@@ -185,7 +239,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
-    if (a.reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
+    if (reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_pre[s]));
       mbar_wait(smem_u32(&s_pre[s]), parity);
@@ -434,7 +488,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
     group_barrier(1 + g, 64);
-    if (a.power == 1) {  // magnitude (stored-spectrogram convention, tfdataset.py:1085-1088): rolled, off the hot path
+    if (magnitude) {  // magnitude (stored-spectrogram convention, tfdataset.py:1085-1088): rolled, off the hot path
       for (int k = t64; k < 64 * NQ; k += 64) {
         const float2 v = pbuf[k];
         pbuf[k] = make_float2(2.0f * sqrtf(v.x), 2.0f * sqrtf(v.y));  // 4 |X|, same weight scale as the power case
@@ -465,18 +519,46 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.w, p23.w, acc_b);
         };
         int i = 0;
+#ifdef CACFE_K1_MEL_SEGLOADS   // A/B switch: all 16-byte loads of a segment (<= 6 quads) issued before its first FMA
+        auto seg = [&](auto nconst) {
+          constexpr int N = decltype(nconst)::value;
+          float4 wv[N], pv[2 * N];
+#pragma unroll
+          for (int u = 0; u < N; ++u) {
+            wv[u] = wq[64 * u];
+            pv[2 * u] = pp[2 * u];
+            pv[2 * u + 1] = pp[2 * u + 1];
+          }
+#pragma unroll
+          for (int u = 0; u < N; ++u) quad(wv[u], pv[2 * u], pv[2 * u + 1]);
+          wq += 64 * N;
+          i = N;
+        };
+        switch (nq) {   // uniform
+          case 1: seg(std::integral_constant<int, 1>()); break;
+          case 2: seg(std::integral_constant<int, 2>()); break;
+          case 3: seg(std::integral_constant<int, 3>()); break;
+          case 4: seg(std::integral_constant<int, 4>()); break;
+          case 5: seg(std::integral_constant<int, 5>()); break;
+          case 6: seg(std::integral_constant<int, 6>()); break;
+          default: break;
+        }
+        if (i == 0)
+#endif
         // (measured alternative: the quad counts of the reference's bank (2 + 5 + 4) as a template parameter and this loop fully
         // unrolled -- 96 fewer SASS instructions, no pointer / counter arithmetic -- 10.11 ms against 9.68 ms per 4096 clips:
         // the scheduler hoists the 33 loads over the accumulate chains, spills more and the phase gets longer, not shorter.)
+        {
 #pragma unroll 1
-        for (; i + 1 < nq; i += 2, wq += 128, pp += 4) {  // two quads per trip: six 16-byte loads in flight
-          const float4 w0 = wq[0], a0 = pp[0], a1 = pp[1], w1 = wq[64], b0 = pp[2], b1 = pp[3];
-          quad(w0, a0, a1);
-          quad(w1, b0, b1);
-        }
-        if (i < nq) {
-          quad(wq[0], pp[0], pp[1]);
-          wq += 64;
+          for (; i + 1 < nq; i += 2, wq += 128, pp += 4) {  // two quads per trip: six 16-byte loads in flight
+            const float4 w0 = wq[0], a0 = pp[0], a1 = pp[1], w1 = wq[64], b0 = pp[2], b1 = pp[3];
+            quad(w0, a0, a1);
+            quad(w1, b0, b1);
+          }
+          if (i < nq) {
+            quad(wq[0], pp[0], pp[1]);
+            wq += 64;
+          }
         }
         if (sg == mj.split_seg) {  // uniform: lanes 2i / 2i+1 hold the two halves of one band
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
