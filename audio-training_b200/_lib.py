@@ -20,8 +20,10 @@ JITTER_LIB_PATH = os.path.join(HERE, "libcacfe_jitter.so")
 SOURCES = ["cacfe.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "cacfe.h")]
 
+# --register-usage-level=7: ptxas has three outcomes for the fused kernel (levels 0-3, 4-5 = default, 6-10); measured with
+# tools/ab_k1.py on the HOT instantiation: 8.52 / 8.44 / 8.28 ms per 4096 clips.  The other kernels change by +-8 instructions.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xptxas", "--register-usage-level=7", "-Xcompiler", "-fPIC", "-shared"]
 
 # enums (include/cacfe.h)
 OK = 0

@@ -34,9 +34,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifndef CACFE_RELAXED_SLEEP_NS
 #define CACFE_RELAXED_SLEEP_NS 800
 #endif
+#ifdef CACFE_WAIT_SUSPEND_NS   // A/B switch: let try_wait suspend the warp for up to this long instead of sleep-polling
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)CACFE_WAIT_SUSPEND_NS)
+        : "memory");
+  } while (!ok);
+}
+#else
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(CACFE_RELAXED_SLEEP_NS);
 }
+#endif
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
