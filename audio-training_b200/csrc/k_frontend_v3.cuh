@@ -40,9 +40,6 @@ constexpr int kHalfStride = 68;                    // floats per half-exchange r
 constexpr int kHalfFloats = 64 * kHalfStride;      // 17408 B per group
 constexpr int kVThreads = kVGroups * 64;
 constexpr int kVTileFrames = 2 * kVGroups;
-#ifdef CACFE_K1_NORM_BATCH
-constexpr int kNormBatch = CACFE_K1_NORM_BATCH;
-#endif   // 16-byte groups loaded before the first is normalised and stored back
 constexpr int kNormIters = 6;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
 
 struct VSmem {
@@ -77,27 +74,6 @@ __device__ __forceinline__ void k1_jitter(unsigned salt) {
 #else
 __device__ __forceinline__ void k1_jitter(unsigned) {}
 #endif
-
-// Fast path of the tile normalisation (whole tile inside the clip): every thread takes up to kNormIters 16-byte groups, all loads
-// first.  A function of its own (A/B switch CACFE_K1_NORM_CALL): the register allocation of the FFT loop does not see it.
-__device__ __noinline__ void k1_normalise_full(float4* t4, int n4, int tid, float mn, float sc, float of) {
-  const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
-  float4 v[kNormIters];
-#pragma unroll
-  for (int u = 0; u < kNormIters; ++u) {
-    const int e = tid + u * kVThreads;
-    if (e < n4) v[u] = t4[e];
-  }
-#pragma unroll
-  for (int u = 0; u < kNormIters; ++u) {
-    const int e = tid + u * kVThreads;
-    if (e < n4) {
-      const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].x, v[u].y), mn2), sc2, of2);
-      const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].z, v[u].w), mn2), sc2, of2);
-      t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
-    }
-  }
-}
 
 // Mel job tables of the plan (mel_jobs.h), device copies.
 struct MelArgs {
@@ -192,10 +168,22 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const int n4 = L.tile_pad >> 2;
     const int e_lo = s_lo < 0 ? (-s_lo) >> 2 : 0, e_hi = (a.n_samples - s_lo) >> 2;
     const cacfe_f2 mn2 = cacfe_pk(mn, mn), sc2 = cacfe_pk(sc, sc), of2 = cacfe_pk(of, of);
+#ifdef CACFE_K1_NORM_ONEPATH   // A/B switch: one unrolled path for every tile (a select per 16-byte group), no second loop
+#pragma unroll
+    for (int u = 0; u < kNormIters; ++u) {
+      const int e = tid + u * kVThreads;
+      if (e < n4) {
+        const float4 v = t4[e];
+        const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v.x, v.y), mn2), sc2, of2);
+        const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v.z, v.w), mn2), sc2, of2);
+        const bool inside = e >= e_lo && e < e_hi;
+        t4[e] = inside ? make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+    }
+#else
     if (e_lo == 0 && e_hi >= n4) {  // the whole tile lies inside the clip (41 of 43 tiles): no padding to write
-#if defined(CACFE_K1_NORM_CALL)
-      k1_normalise_full(t4, n4, tid, mn, sc, of);
-#elif !defined(CACFE_K1_NORM_BATCH)   // load, normalise, store one 16-byte group at a time
+      // (measured alternatives, tools/ab_k1.py: all six loads before the first store, a software pipeline of depth 1 - 3, the
+      // loop as a function of its own -- each is 4 - 8 % slower: more instructions in the loop body, or a stack frame)
 #pragma unroll
       for (int u = 0; u < kNormIters; ++u) {
         const int e = tid + u * kVThreads;
@@ -206,28 +194,6 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
         }
       }
-#else
-      // all loads first: the stores go through the same pointer, so the compiler will not move a later load above them, and
-      // every group would pay the shared-memory latency (the FFT registers are dead here: 24 registers are free)
-#pragma unroll
-      for (int u0 = 0; u0 < kNormIters; u0 += kNormBatch) {
-        float4 v[kNormBatch];
-#pragma unroll
-        for (int u = 0; u < kNormBatch; ++u) {
-          const int e = tid + (u0 + u) * kVThreads;
-          if (e < n4) v[u] = t4[e];
-        }
-#pragma unroll
-        for (int u = 0; u < kNormBatch; ++u) {
-          const int e = tid + (u0 + u) * kVThreads;
-          if (e < n4) {
-            const cacfe_f2 lo = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].x, v[u].y), mn2), sc2, of2);
-            const cacfe_f2 hi = cacfe_fma2(cacfe_sub2(cacfe_pk(v[u].z, v[u].w), mn2), sc2, of2);
-            t4[e] = make_float4(cacfe_lo(lo), cacfe_hi(lo), cacfe_lo(hi), cacfe_hi(hi));
-          }
-        }
-      }
-#endif
     } else {
 #pragma unroll 1
       for (int e = tid; e < n4; e += kVThreads) {
@@ -239,6 +205,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
+#endif
     if (reflect) {  // numpy 'reflect' (no edge repeat): copy the already normalised mirror samples
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_pre[s]));
