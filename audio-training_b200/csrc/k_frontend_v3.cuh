@@ -40,7 +40,10 @@ constexpr int kHalfStride = 68;                    // floats per half-exchange r
 constexpr int kHalfFloats = 64 * kHalfStride;      // 17408 B per group
 constexpr int kVThreads = kVGroups * 64;
 constexpr int kVTileFrames = 2 * kVGroups;
-constexpr int kNormIters = 6;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
+#ifndef CACFE_K1_NORM_ITERS
+#define CACFE_K1_NORM_ITERS 6
+#endif
+constexpr int kNormIters = CACFE_K1_NORM_ITERS;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
 
 struct VSmem {
   int tile_len, tile_pad, mel_quads;
@@ -184,7 +187,11 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     if (e_lo == 0 && e_hi >= n4) {  // the whole tile lies inside the clip (41 of 43 tiles): no padding to write
       // (measured alternatives, tools/ab_k1.py: all six loads before the first store, a software pipeline of depth 1 - 3, the
       // loop as a function of its own -- each is 4 - 8 % slower: more instructions in the loop body, or a stack frame)
+#ifdef CACFE_K1_NORM_UNROLLED   // A/B switch; rolled is 112 instructions shorter and 0.9 % faster (8.30 -> 8.22 ms)
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
       for (int u = 0; u < kNormIters; ++u) {
         const int e = tid + u * kVThreads;
         if (e < n4) {
@@ -467,11 +474,22 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     {
       const float4* p4 = reinterpret_cast<const float4*>(pbuf);
       const float4* wq = s_melw + t64;
+#ifdef CACFE_K1_MEL_ROLLED   // A/B switch: one copy of the segment body (rolled over the segments), each band stored as it completes
+      float* const o_btm = a.out + ((size_t)b_cur * a.n_frames + ta) * a.n_mels;
+      float* const o_img = a.out + ((size_t)b_cur * a.n_mels * a.n_frames + ta) * a.channels;
+#pragma unroll 1
+      for (int sg = 0; sg < kMelMaxSeg; ++sg) {
+#else
       float ra[kMelMaxSeg], rb[kMelMaxSeg];
       int dsc[kMelMaxSeg];
 #pragma unroll
       for (int sg = 0; sg < kMelMaxSeg; ++sg) {
+#endif
+#ifdef CACFE_K1_MEL_ROLLED   // (a run-time index into the parameter array would copy it to local memory)
+        const int nq = sg == 0 ? mj.nq[0] : (sg == 1 ? mj.nq[1] : mj.nq[2]);
+#else
         const int nq = mj.nq[sg];                      // uniform
+#endif
         const int d = s_desc[sg * 64 + t64];
         const float4* pp = p4 + ((d >> 8) & 0xffff);   // first 16-byte chunk: (A[k], B[k], A[k+1], B[k+1])
         float acc_a = 0.0f, acc_b = 0.0f;
@@ -486,32 +504,6 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_b = fmaf(wv.w, p23.w, acc_b);
         };
         int i = 0;
-#ifdef CACFE_K1_MEL_SEGLOADS   // A/B switch: all 16-byte loads of a segment (<= 6 quads) issued before its first FMA
-        auto seg = [&](auto nconst) {
-          constexpr int N = decltype(nconst)::value;
-          float4 wv[N], pv[2 * N];
-#pragma unroll
-          for (int u = 0; u < N; ++u) {
-            wv[u] = wq[64 * u];
-            pv[2 * u] = pp[2 * u];
-            pv[2 * u + 1] = pp[2 * u + 1];
-          }
-#pragma unroll
-          for (int u = 0; u < N; ++u) quad(wv[u], pv[2 * u], pv[2 * u + 1]);
-          wq += 64 * N;
-          i = N;
-        };
-        switch (nq) {   // uniform
-          case 1: seg(std::integral_constant<int, 1>()); break;
-          case 2: seg(std::integral_constant<int, 2>()); break;
-          case 3: seg(std::integral_constant<int, 3>()); break;
-          case 4: seg(std::integral_constant<int, 4>()); break;
-          case 5: seg(std::integral_constant<int, 5>()); break;
-          case 6: seg(std::integral_constant<int, 6>()); break;
-          default: break;
-        }
-        if (i == 0)
-#endif
         // (measured alternative: the quad counts of the reference's bank (2 + 5 + 4) as a template parameter and this loop fully
         // unrolled -- 96 fewer SASS instructions, no pointer / counter arithmetic -- 10.11 ms against 9.68 ms per 4096 clips:
         // the scheduler hoists the 33 loads over the accumulate chains, spills more and the phase gets longer, not shorter.)
@@ -531,6 +523,22 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           acc_a += __shfl_xor_sync(kFullMask, acc_a, 1);
           acc_b += __shfl_xor_sync(kFullMask, acc_b, 1);
         }
+#ifdef CACFE_K1_MEL_ROLLED
+        if ((d >> 25) & 1) {
+          if (LAYOUT == LAYOUT_BTM) {
+            o_btm[d & 0xff] = acc_a;
+            if (store_b) o_btm[a.n_mels + (d & 0xff)] = acc_b;
+          } else {
+            float* o = o_img + (size_t)(d & 0xff) * a.n_frames * a.channels;
+#pragma unroll 1
+            for (int ch = 0; ch < a.channels; ++ch) {
+              o[ch] = acc_a;
+              if (store_b) o[a.channels + ch] = acc_b;
+            }
+          }
+        }
+      }
+#else
         ra[sg] = acc_a;
         rb[sg] = acc_b;
         dsc[sg] = d;
@@ -557,6 +565,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
             }
           }
       }
+#endif
     }
     // (the next trip's exchange stores come after release_tile's group barrier: the powers have been consumed by then)
   }
