@@ -93,7 +93,8 @@ struct MelArgs {
 // WINC: the Hann(4096) window is computed per thread by angle addition (two FFMA with immediates per value) instead of being
 // read from shared memory (one LDS.64 per two values): the kernel is shared-memory-wavefront bound, not FMA bound.  Shorter
 // transforms (zero-padded window) keep the table.
-// HOT: the instantiation of the benchmarked path (per-clip normalisation on, no reflect padding, power 2) with those three run-time
+// HOT: the instantiation of the benchmarked path (per-clip normalisation on, no reflect padding, power 2; for the spectrogram
+// layout power 1 = the stored magnitude of audiodataset.load_data) with those three run-time
 // switches resolved at compile time: the magnitude loop with its sqrt calls, the mirror pass and the un-normalised form leave
 // the code the twelve warps fetch.
 template <int NQ, int LAYOUT, bool WINC = false, bool HOT = false>
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
   extern __shared__ __align__(128) unsigned char smem[];
   const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
   const bool has_norm = HOT || a.norm != nullptr, reflect = !HOT && a.reflect, magnitude = !HOT && a.power == 1;
+  const bool spec_magnitude = HOT || a.power == 1;   // LAYOUT_SPEC only
   float4* s_tw4 = reinterpret_cast<float4*>(smem);   // [32 output pairs][64 n2]
   float2* s_win2 = reinterpret_cast<float2*>(smem + L.off_win);
   float* s_tile = reinterpret_cast<float*>(smem + L.off_tile);
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           const float zr = re[q], zi = im[q];
           const float ar = zr + pr, ai = zi - pi, br = zr - pr, bi = zi + pi;
           float va = fmaf(ar, ar, ai * ai), vb = fmaf(br, br, bi * bi);   // 4 |XA|^2, 4 |XB|^2
-          if (a.power == 1) {
+          if (spec_magnitude) {
             va = 0.5f * sqrt_approx(va);
             vb = 0.5f * sqrt_approx(vb);
           } else {
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           // Nyquist bin k = 2048 = row 0, q = 32: Z[2048] pairs with itself
           const float zr = re[32], zi = im[32];
           float va = 4.0f * zr * zr, vb = 4.0f * zi * zi;
-          if (a.power == 1) {
+          if (spec_magnitude) {
             va = 0.5f * sqrt_approx(va);
             vb = 0.5f * sqrt_approx(vb);
           } else {
