@@ -443,15 +443,16 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok) {
-    const void* kernels[12] = {
+    const void* kernels[13] = {
 #define CACFE_V3_K(NQ_, LAYOUT_) (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false>, (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true>
         CACFE_V3_K(33, cacfe::LAYOUT_SPEC), CACFE_V3_K(15, cacfe::LAYOUT_BTM), CACFE_V3_K(15, cacfe::LAYOUT_BMTC),
         CACFE_V3_K(33, cacfe::LAYOUT_BTM), CACFE_V3_K(33, cacfe::LAYOUT_BMTC),
-        (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, true>,
-        (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, true>
+        (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 1>,
+        (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 2>,
+        (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1>
 #undef CACFE_V3_K
     };
-    for (int q = 0; q < 12 && e == cudaSuccess; ++q)
+    for (int q = 0; q < 13 && e == cudaSuccess; ++q)
       // the attribute belongs to the function, not to the plan: always the device maximum, so that a plan created later
       // with a smaller layout cannot shrink it under an earlier plan
       e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -729,11 +730,15 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     else cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);        \
   } while (0)
     if (layout == cacfe::LAYOUT_SPEC && winc && a.norm != nullptr && !a.reflect && a.power == 1)   // audiodataset.load_data's configuration
-      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, true><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (layout == cacfe::LAYOUT_SPEC)
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPEC);
     else if (p->nq_v3 <= 15 && btm && winc && a.norm != nullptr && !a.reflect && a.power == 2)   // the benchmarked configuration
-      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, true><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+#ifndef CACFE_NO_HOT2
+    else if (p->nq_v3 <= 15 && btm && winc && a.norm == nullptr && !a.reflect && a.power == 2)   // raw_to_mel / get_spect on normalised clips
+      cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 2><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+#endif
     else if (p->nq_v3 <= 15 && btm)
       CACFE_V3_LAUNCH(15, cacfe::LAYOUT_BTM);
     else if (p->nq_v3 <= 15)

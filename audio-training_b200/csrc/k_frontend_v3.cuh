@@ -93,16 +93,17 @@ struct MelArgs {
 // WINC: the Hann(4096) window is computed per thread by angle addition (two FFMA with immediates per value) instead of being
 // read from shared memory (one LDS.64 per two values): the kernel is shared-memory-wavefront bound, not FMA bound.  Shorter
 // transforms (zero-padded window) keep the table.
-// HOT: the instantiation of the benchmarked path (per-clip normalisation on, no reflect padding, power 2; for the spectrogram
+// HOT = 1: the instantiation of the benchmarked path (per-clip normalisation on, no reflect padding, power 2; for the spectrogram
 // layout power 1 = the stored magnitude of audiodataset.load_data) with those three run-time
 // switches resolved at compile time: the magnitude loop with its sqrt calls, the mirror pass and the un-normalised form leave
 // the code the twelve warps fetch.
-template <int NQ, int LAYOUT, bool WINC = false, bool HOT = false>
+template <int NQ, int LAYOUT, bool WINC = false, int HOT = 0>   // HOT: 0 generic, 1 normalisation on, 2 normalisation off
 __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const FrontendArgs a, const MelArgs mj,
                                                                       const int total_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const VSmem L = v3_smem_layout(a.hop, mj.total_quads);
-  const bool has_norm = HOT || a.norm != nullptr, reflect = !HOT && a.reflect, magnitude = !HOT && a.power == 1;
+  // (HOT = 2: the same with the normalisation off -- raw_to_mel / get_spect on clips the caller has normalised, tfdataset.py:913-915)
+  const bool has_norm = HOT == 1 || (HOT == 0 && a.norm != nullptr), reflect = !HOT && a.reflect, magnitude = !HOT && a.power == 1;
   const bool spec_magnitude = HOT || a.power == 1;   // LAYOUT_SPEC only
   float4* s_tw4 = reinterpret_cast<float4*>(smem);   // [32 output pairs][64 n2]
   float2* s_win2 = reinterpret_cast<float2*>(smem + L.off_win);
