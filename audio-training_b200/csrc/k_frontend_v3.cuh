@@ -21,6 +21,14 @@
 // (tf.signal.stft(1024 | 2048, ...) of raw_to_mel_rgb / raw_to_mel_dual, tfdataset.py:1818-2004).  r x the FFT work of a
 // dedicated kernel; those variants are not on the benchmarked path.
 // Sample tiles still arrive by TMA bulk copy (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a 2-deep ring.
+//
+// Round 2 (DESIGN.md 3.1a'): what bound this kernel was again the instruction fetch path (47.6 KB of loop body against a 32 KB
+// instruction cache) and spilled registers (168 per thread, and with 220 KB of shared memory no L1 to catch a spill).  Three
+// changes without any arithmetic in them took it from 9.67 to 8.2 ms per 4096 clips: the FFT-group index goes through a lane-0
+// broadcast so that ptxas keeps everything derived from it in uniform registers; the benchmarked configurations have their own
+// instantiations (template parameter HOT) with the run-time switches resolved; the library is built with ptxas
+// --register-usage-level=7.  The kernel is sensitive to both: any edit must be checked with -Xptxas -v (spills) and timed
+// (tools/ab_k1.py) -- shorter source is not faster code here.
 #pragma once
 #include "cacfe_common.cuh"
 #include "frontend_core.cuh"
