@@ -122,8 +122,9 @@ class Plan:
         return int(self._lib.cacfe_plan_launch_count(self._handle))
 
     def force_generic(self, enable=True):
-        """Use the generic (non-streaming) fused kernel even where the TMA streaming form applies."""
-        _lib.check(self._lib.cacfe_plan_force_generic(self._handle, 1 if enable else 0))
+        """True / 1: use the generic (non-streaming) fused kernel even where the TMA streaming form applies; 2: the streaming
+        kernel without its compile-time specialisations (HOT instantiations) of the common configurations."""
+        _lib.check(self._lib.cacfe_plan_force_generic(self._handle, int(enable)))
 
     def profile(self, enable=True):
         _lib.check(self._lib.cacfe_plan_profile(self._handle, 1 if enable else 0))

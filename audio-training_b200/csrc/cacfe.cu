@@ -85,6 +85,7 @@ struct cacfe_plan {
   size_t smem_optin = 0, smem_per_sm = 0;
   bool v3_ok = false;
   bool force_generic = false;  // tests: run the non-streaming kernel on configurations that allow both
+  bool no_hot = false;         // tests: the streaming kernel without its HOT instantiations (cacfe_plan_force_generic(plan, 2))
   bool frontend_ok = false;
   std::atomic<long long> launches{0};
   // optional CUDA-event bracket around every K1 launch (bench.py's live per-kernel timing)
@@ -512,7 +513,8 @@ int cacfe_plan_profile_read(cacfe_plan* p, double* k1_ms, long long* k1_launches
 
 int cacfe_plan_force_generic(cacfe_plan* p, int enable) {
   if (!p) return fail(CACFE_EINVAL, "plan_force_generic: null plan");
-  p->force_generic = enable != 0;
+  p->force_generic = enable == 1;
+  p->no_hot = enable == 2;
   return CACFE_OK;
 }
 
@@ -729,16 +731,15 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
     if (winc) cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);    \
     else cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);        \
   } while (0)
-    if (layout == cacfe::LAYOUT_SPEC && winc && a.norm != nullptr && !a.reflect && a.power == 1)   // audiodataset.load_data's configuration
+    const bool hot = !p->no_hot;
+    if (hot && layout == cacfe::LAYOUT_SPEC && winc && a.norm != nullptr && !a.reflect && a.power == 1)   // audiodataset.load_data's configuration
       cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (layout == cacfe::LAYOUT_SPEC)
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPEC);
-    else if (p->nq_v3 <= 15 && btm && winc && a.norm != nullptr && !a.reflect && a.power == 2)   // the benchmarked configuration
+    else if (hot && p->nq_v3 <= 15 && btm && winc && a.norm != nullptr && !a.reflect && a.power == 2)   // the benchmarked configuration
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
-#ifndef CACFE_NO_HOT2
-    else if (p->nq_v3 <= 15 && btm && winc && a.norm == nullptr && !a.reflect && a.power == 2)   // raw_to_mel / get_spect on normalised clips
+    else if (hot && p->nq_v3 <= 15 && btm && winc && a.norm == nullptr && !a.reflect && a.power == 2)   // raw_to_mel / get_spect on normalised clips
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 2><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
-#endif
     else if (p->nq_v3 <= 15 && btm)
       CACFE_V3_LAUNCH(15, cacfe::LAYOUT_BTM);
     else if (p->nq_v3 <= 15)

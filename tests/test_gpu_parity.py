@@ -225,6 +225,22 @@ def test_fused_kernel_edge_clips(oracle, clips, bank, framing):
                     assert np.isfinite(ga).all()
 
 
+def test_k1_specialisations_bit_identical(oracle):
+    """The fused kernel has compile-time specialisations (HOT instantiations) of the common configurations -- normalisation on /
+    off with the [B,T,M] layout, and the stored-spectrogram producer: the same launch without them (force_generic(2)) must give
+    the same bits."""
+    x = torch.from_numpy(oracle.synth_clips(np.arange(40))).cuda()
+    for kw in (dict(normalize=True, channels=1, out_layout="btm"), dict(normalize=False, channels=1, out_layout="btm"),
+               dict(normalize=True, channels=3, out_layout="bmtc")):
+        hot, plain = rt.Plan(rt.FrontendConfig(**kw), 0), rt.Plan(rt.FrontendConfig(**kw), 0)
+        plain.force_generic(2)
+        assert torch.equal(hot.frontend(x), plain.frontend(x)), kw
+    kw = dict(framing="center_zero", power=1, channels=1, normalize=True)
+    hot, plain = rt.Plan(rt.FrontendConfig(**kw), 0), rt.Plan(rt.FrontendConfig(**kw), 0)
+    plain.force_generic(2)
+    assert torch.equal(hot.stft(x), plain.stft(x))
+
+
 def test_k1_jitter():
     """Stand-in for racecheck (compute-sanitizer is closed on this pool): libcacfe_jitter.so is the same library built with
     -DCACFE_K1_JITTER, which puts a pseudo-random pause of 0..2 us before every hand-over operation of the persistent fused
