@@ -62,7 +62,9 @@ constexpr int kEmaUnroll = 8;
 template <int MODE>
 __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
   __shared__ float scratch[64];
-  const int clip = blockIdx.y;
+  // REDUCE walks the clips from the last to the first and APPLY from the first to the last: what the producer wrote last (and
+  // what REDUCE read last) is still in the 126 MB L2 when the next pass starts there
+  const int clip = MODE == PCEN_REDUCE ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;  // row inside the clip
   const bool live = r < a.rows_per_clip;
   float mn = INFINITY, mx = -INFINITY;
