@@ -51,7 +51,11 @@ constexpr int kVTileFrames = 2 * kVGroups;
 #ifndef CACFE_K1_NORM_ITERS
 #define CACFE_K1_NORM_ITERS 6
 #endif
-constexpr int kNormIters = CACFE_K1_NORM_ITERS;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
+constexpr int kNormIters = CACFE_K1_NORM_ITERS;
+#ifndef CACFE_K1_NORM_UNROLL   // A/B switch; rolled (1) is 112 instructions shorter than fully unrolled (6) and 0.9 % faster
+#define CACFE_K1_NORM_UNROLL 1
+#endif
+constexpr int kNormUnroll = CACFE_K1_NORM_UNROLL;    // 16-byte groups per thread in the normalise pass: tiles up to 6 * 384 * 4 samples (hop <= 464)
 
 struct VSmem {
   int tile_len, tile_pad, mel_quads;
@@ -198,11 +202,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     if (e_lo == 0 && e_hi >= n4) {  // the whole tile lies inside the clip (41 of 43 tiles): no padding to write
       // (measured alternatives, tools/ab_k1.py: all six loads before the first store, a software pipeline of depth 1 - 3, the
       // loop as a function of its own -- each is 4 - 8 % slower: more instructions in the loop body, or a stack frame)
-#ifdef CACFE_K1_NORM_UNROLLED   // A/B switch; rolled is 112 instructions shorter and 0.9 % faster (8.30 -> 8.22 ms)
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
+#pragma unroll kNormUnroll
       for (int u = 0; u < kNormIters; ++u) {
         const int e = tid + u * kVThreads;
         if (e < n4) {
