@@ -444,16 +444,17 @@ int cacfe_plan_create(const cacfe_config* cfg, int device, cacfe_plan** out) {
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_tw4, tw4.data(), tw4.size() * sizeof(float));
   if (e == cudaSuccess && p->v3_ok) e = upload((void**)&p->d_mel_desc, p->jobs.desc.data(), p->jobs.desc.size() * sizeof(int));
   if (e == cudaSuccess && p->v3_ok) {
-    const void* kernels[13] = {
+    const void* kernels[16] = {
 #define CACFE_V3_K(NQ_, LAYOUT_) (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, false>, (const void*)cacfe::stft_mel_v3_kernel<NQ_, LAYOUT_, true>
         CACFE_V3_K(33, cacfe::LAYOUT_SPEC), CACFE_V3_K(15, cacfe::LAYOUT_BTM), CACFE_V3_K(15, cacfe::LAYOUT_BMTC),
         CACFE_V3_K(33, cacfe::LAYOUT_BTM), CACFE_V3_K(33, cacfe::LAYOUT_BMTC),
         (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 1>,
         (const void*)cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 2>,
-        (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1>
+        (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1>,
+        CACFE_V3_K(33, cacfe::LAYOUT_SPECT), (const void*)cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPECT, true, 1>
 #undef CACFE_V3_K
     };
-    for (int q = 0; q < 13 && e == cudaSuccess; ++q)
+    for (int q = 0; q < 16 && e == cudaSuccess; ++q)
       // the attribute belongs to the function, not to the plan: always the device maximum, so that a plan created later
       // with a smaller layout cannot shrink it under an earlier plan
       e = cudaFuncSetAttribute(kernels[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -736,6 +737,10 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
       cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPEC, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (layout == cacfe::LAYOUT_SPEC)
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPEC);
+    else if (hot && layout == cacfe::LAYOUT_SPECT && winc && a.norm != nullptr && !a.reflect && a.power == 1)
+      cacfe::stft_mel_v3_kernel<33, cacfe::LAYOUT_SPECT, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
+    else if (layout == cacfe::LAYOUT_SPECT)
+      CACFE_V3_LAUNCH(33, cacfe::LAYOUT_SPECT);
     else if (hot && p->nq_v3 <= 15 && btm && winc && a.norm != nullptr && !a.reflect && a.power == 2)   // the benchmarked configuration
       cacfe::stft_mel_v3_kernel<15, cacfe::LAYOUT_BTM, true, 1><<<ctas, cacfe::kVThreads, p->kv.total, st>>>(a, mj, (int)tiles);
     else if (hot && p->nq_v3 <= 15 && btm && winc && a.norm == nullptr && !a.reflect && a.power == 2)   // raw_to_mel / get_spect on normalised clips
@@ -750,7 +755,7 @@ static int launch_frontend(cacfe_plan* p, const float* raw, float* feat, int B, 
       CACFE_V3_LAUNCH(33, cacfe::LAYOUT_BMTC);
 #undef CACFE_V3_LAUNCH
   } else {
-    if (layout == cacfe::LAYOUT_SPEC)
+    if (layout == cacfe::LAYOUT_SPEC || layout == cacfe::LAYOUT_SPECT)
       return fail(CACFE_EINVAL, "stft: the spectrogram output needs the persistent kernel (16-byte aligned input, n_samples %% 4 == 0)");
     if (!p->frontend_ok)
       return fail(CACFE_EINVAL, "frontend: n_fft=%d needs the persistent kernel (16-byte aligned input, not forced generic)",
@@ -805,6 +810,19 @@ int cacfe_stft_stats(cacfe_plan* p, const float* raw, float* spec, float* range_
   cudaStream_t st = (cudaStream_t)stream;
   float* staging = (float*)((char*)ws + frontend_ws_bytes(B));
   const size_t per_clip = (size_t)p->n_bins * p->n_frames;
+  static const bool staged = getenv("CACFE_STFT_STAGED") != nullptr;   // A/B: the two-kernel form (staging + transpose)
+  if (!staged) {
+    // the fused kernel writes the stored [b][k][t] layout itself (LAYOUT_SPECT): no staging buffer, no second pass
+    for (int b0 = 0; b0 < B; b0 += 16384) {   // keeps the tile count inside the kernel's int arithmetic
+      const int nb = B - b0 < 16384 ? B - b0 : 16384;
+      int rc = launch_frontend(p, raw + (size_t)b0 * p->cfg.n_samples, spec + (size_t)b0 * per_clip, nb, cacfe::LAYOUT_SPECT, 1, ws, st);
+      if (rc != CACFE_OK) return rc;
+      if (range_min)
+        CUDA_TRY(cudaMemcpyAsync(range_min + 2 * (size_t)b0, (char*)ws + align256((size_t)nb * kMaxSplits * sizeof(float2)),
+                                 (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
+    return CACFE_OK;
+  }
   for (int b0 = 0; b0 < B; b0 += kStftChunk) {  // [b][t][k] staging (coalesced from the FFT kernel), then the transpose
     const int nb = B - b0 < kStftChunk ? B - b0 : kStftChunk;
     int rc = launch_frontend(p, raw + (size_t)b0 * p->cfg.n_samples, staging, nb, cacfe::LAYOUT_SPEC, 1, ws, st);

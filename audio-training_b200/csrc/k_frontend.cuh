@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
 // K1
 // ------------------------------------------------------------------------------------------------
 enum : int { FRAME_TF_PAD_END = 0, FRAME_CENTER_ZERO = 1, FRAME_CENTER_REFLECT = 2, FRAME_NO_PAD = 3 };
-enum : int { LAYOUT_BMTC = 0, LAYOUT_BTM = 1, LAYOUT_SPEC = 2 };  // SPEC: spectrogram [B][K][T], persistent kernel only
+enum : int { LAYOUT_BMTC = 0, LAYOUT_BTM = 1, LAYOUT_SPEC = 2, LAYOUT_SPECT = 3 };  // persistent kernel only: SPEC = spectrogram staged as
+                                                                                    // [B][T][K], SPECT = written as the stored [B][K][T]
 
 struct FrontendArgs {
   const float* in;         // [B][n_samples]

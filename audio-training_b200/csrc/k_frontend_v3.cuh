@@ -310,7 +310,28 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
     const int b_cur = b;
     b = b_next;
     t0 = t_next;
-    if (ta >= a.n_frames) {  // group-uniform
+    // LAYOUT_SPECT: the six groups leave (|XA|, |XB|) of their frame pairs in their exchange tiles [k], the CTA meets, and all
+    // threads write the tile's 12 frames as 48-byte runs of the stored [b][k][t] array (the neighbouring tiles of the clip are in
+    // flight on the neighbouring CTAs: L2 sees whole lines); a second rendezvous hands the exchange tiles back to the FFT.
+    auto spect_store = [&]() {
+      __syncthreads();
+      const int t_first = ta - 2 * g, n_out = mj.spec_bins;
+      const int rsh = 31 - __clz(mj.spec_ratio);
+      const int n_t = min(kVTileFrames, a.n_frames - t_first);
+      float* const obase = a.out + (size_t)b_cur * n_out * a.n_frames + t_first;
+      // thread -> (frame tt of the tile, rows k0, k0 + 32, ...): twelve neighbouring lanes write one 48-byte run
+      const int tt = tid % kVTileFrames, k0 = tid / kVTileFrames;
+      const float* src = s_exch + (tt >> 1) * kHalfFloats + (tt & 1);
+      float* dst = obase + tt;
+      if (tt < n_t) {
+#pragma unroll 4
+        for (int ko = k0; ko < n_out; ko += kVThreads / kVTileFrames) dst[(size_t)ko * a.n_frames] = src[2 * (ko << rsh)];
+      }
+      __syncthreads();
+    };
+    // (LAYOUT_SPECT: a group whose frames lie past the end of the clip -- one or two groups in the last of a clip's 43 tiles --
+    // transforms whatever its part of the tile holds and stores nothing: every thread reaches the one spect_store below)
+    if (LAYOUT != LAYOUT_SPECT && ta >= a.n_frames) {  // group-uniform
       release_tile(i);
       continue;
     }
@@ -402,7 +423,7 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
       }
     }
 
-    if (LAYOUT == LAYOUT_SPEC) {
+    if (LAYOUT == LAYOUT_SPEC || LAYOUT == LAYOUT_SPECT) {
       // ---- spectrogram output (audiodataset.load_data, audiodataset.py:1302-1303): |X| (power 1) or |X|^2 of every bin
       // of an n_fft-point transform; bins of the 4096-point grid that are not multiples of `ratio` belong to no bin of
       // the shorter transform.
@@ -431,7 +452,9 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
             vb *= 0.25f;
           }
           const int k = j + 64 * q;
-          if ((k & rmask) == 0) {
+          if (LAYOUT == LAYOUT_SPECT) {
+            pbuf[k] = make_float2(va, vb);
+          } else if ((k & rmask) == 0) {
             float* o = obase + (k >> rsh);
             o[0] = va;
             if (store_b) o[n_out] = vb;
@@ -447,11 +470,16 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
             va *= 0.25f;
             vb *= 0.25f;
           }
-          float* o = obase + (2048 >> rsh);
-          o[0] = va;
-          if (store_b) o[n_out] = vb;
+          if (LAYOUT == LAYOUT_SPECT) {
+            pbuf[2048] = make_float2(va, vb);
+          } else {
+            float* o = obase + (2048 >> rsh);
+            o[0] = va;
+            if (store_b) o[n_out] = vb;
+          }
         }
       }
+      if (LAYOUT == LAYOUT_SPECT) spect_store();
       continue;
     }
     // ---- split the two frames, power: bin k = j + 64 q goes to pbuf[k] as (4 |XA|^2, 4 |XB|^2) -------------------------

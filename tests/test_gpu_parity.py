@@ -271,6 +271,12 @@ for name, cfg, reps, nb in (("pad_end", rt.FrontendConfig(normalize=True, channe
         same += int(torch.equal(plan.frontend(x[:nb]), first))
     res[name] = {"runs": reps, "identical": same, "crc": zlib.crc32(first.cpu().numpy().tobytes()),
                  "finite": bool(torch.isfinite(first).all())}
+# the stored-spectrogram producer: the same hand-overs plus two CTA-wide rendezvous per tile around the [b][k][t] store
+plan = rt.Plan(rt.FrontendConfig(framing="center_zero", power=1, channels=1, normalize=True), 0)
+first = plan.stft(x[:256]).clone()
+same = sum(int(torch.equal(plan.stft(x[:256]), first)) for _ in range(int(sys.argv[3])))
+res["stft"] = {"runs": int(sys.argv[3]), "identical": same, "crc": zlib.crc32(first.cpu().numpy().tobytes()),
+               "finite": bool(torch.isfinite(first).all())}
 print(json.dumps(res))
 """
     env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -280,7 +286,7 @@ print(json.dumps(res))
         assert r.returncode == 0, r.stderr[-2000:]
         out[lib] = json.loads(r.stdout.strip().splitlines()[-1])
     jit, plain = out[_lib.JITTER_LIB_PATH], out[_lib.LIB_PATH]
-    for k in ("pad_end", "reflect"):
+    for k in ("pad_end", "reflect", "stft"):
         assert jit[k]["finite"] and jit[k]["identical"] == jit[k]["runs"], (k, jit[k])
         assert jit[k]["crc"] == plain[k]["crc"], (k, jit[k], plain[k])
 
