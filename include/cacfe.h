@@ -149,7 +149,7 @@ int cacfe_frontend(cacfe_plan* plan, const float* raw_dev, float* feat_dev, int 
 /* ---- next row 1: the stored `audio/spectogram` field.  np.abs(librosa.stft(normed, n_fft, hop)) of
  * audiodataset.load_data (audiodataset.py:1301-1303) with framing CENTER_*, power 1, normalize 1; any framing / power
  * of the plan otherwise.  raw_dev [B][n_samples] -> spec_dev [B][n_fft/2+1][T] (t contiguous, what path C reads). */
-size_t cacfe_stft_workspace_bytes(const cacfe_plan* plan, int B); /* includes a 64-clip [t][k] staging buffer */
+size_t cacfe_stft_workspace_bytes(const cacfe_plan* plan, int B);
 int cacfe_stft(cacfe_plan* plan, const float* raw_dev, float* spec_dev, int B, void* workspace_dev, void* stream);
 /* the same, and (plans with normalize = 1) range_min_dev [B][2] receives each clip's (max - min, min): max - min == 0 is the
  * reference's silent-window test  a_max == a_min  (audiodataset.py:1311-1323), answered by the pass the normalisation
