@@ -30,6 +30,43 @@ def test_library_exports_every_declared_symbol():
     assert lib.cacfe_version() == 103
 
 
+def test_plain_c_caller(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit that includes include/cacfe.h compiles without warnings, links against
+    libcacfe.so and calls the host-only entry points (version, filterbank, error text, workspace arithmetic).  No GPU needed."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "cacfe.h"
+int main(void) {
+  if (cacfe_version() != CACFE_VERSION) return 1;
+  float* bank = (float*)calloc(160 * 2049, sizeof(float));
+  if (cacfe_mel_filterbank(48000, 160, 100.0, 11000.0, 4096, 1000.0, bank) != 0) return 2;
+  int nnz = 0;
+  for (int i = 0; i < 160 * 2049; ++i) nnz += bank[i] != 0.0f;
+  if (cacfe_mel_filterbank(48000, 0, 100.0, 11000.0, 4096, 1000.0, bank) == 0) return 3;   /* bad argument -> status code */
+  if (cacfe_last_error()[0] == 0) return 4;
+  if (cacfe_pcen_workspace_bytes(4, 1, 160) == 0 || cacfe_compress_workspace_bytes(1, 1000) == 0) return 5;
+  printf("%d\n", nnz);
+  free(bank);
+  return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    _lib.load()
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lcacfe", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert int(r.stdout) == 1844          # SURVEY 8a4: non-zeros of the fmin = 100 bank
+
+
 def test_native_filterbank_matches_reference_goldens(golden_banks):
     lib = _lib.load()
     for tag in [k for k in golden_banks.files if not k.endswith("_args")]:
