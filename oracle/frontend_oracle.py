@@ -29,7 +29,8 @@ under ``tests/golden/``):
     with its Butterworth pre-filter (gen_filter_golden.py), ``identifytracks.signal_noise``
     (gen_signal_golden.py) and the two model builders ``badwinner2.build_model`` /
     ``wr_resnet_bird.WRResNet`` over an eager numpy Keras stand-in (gen_consumer_golden.py)
-    are executed from their own source in the same way.
+    are executed from their own source in the same way; so are ``ExponentialMovingAverage`` with an explicit
+    initial state and ``get_spect(mean_sub=True)`` (gen_golden.py).
 The TensorFlow / librosa / Keras *internals* (framing, window, FFT, scan, layer semantics)
 remain restated from documentation: for those, parity is UNPINNED and says so in DESIGN.md.
 (``tf.signal.hann_window`` is evaluated in float32 by TensorFlow; this module's float64
