@@ -52,6 +52,13 @@ class Gen:
         self.emit(f"const cacfe_f2 {d} = cacfe_mul2({a}, sq2);")
         return d
 
+    def fmasq(self, a, c, neg=False):
+        """c + a / sqrt2 (or c - a / sqrt2): one packed FMA with a constant operand -- it costs what the packed add costs
+        (tools/ubench_issue.cu: 2.07 cycles against 2.08) and the multiply by 1 / sqrt2 disappears."""
+        d = self.new()
+        self.emit(f"const cacfe_f2 {d} = cacfe_fma2({a}, {'nsq2' if neg else 'sq2'}, {c});")
+        return d
+
 
 def radix8(g, xr, xi):
     """Packed natural-order radix-8 DIF butterfly.  xr/xi: 8 packed names each.  Returns (yr, yi) lists for k = 0..7.
@@ -62,28 +69,32 @@ def radix8(g, xr, xi):
         ai.append(g.add(xi[i], xi[i + 4]))
         br.append(g.sub(xr[i], xr[i + 4]))
         bi.append(g.sub(xi[i], xi[i + 4]))
-    # odd branch: c0 = b0; c1 = b1 * (1 - i)/sqrt2; c2 = b2 * (-i); c3 = b3 * (-1 - i)/sqrt2
-    c1r = g.mulsq(g.add(br[1], bi[1]))
-    c1i = g.mulsq(g.sub(bi[1], br[1]))
-    # c2 = (b2i, -b2r)
-    # c3 = ((b3i - b3r) SQ, -(b3r + b3i) SQ): keep n3i = (b3r + b3i) SQ and remember the minus sign
-    c3r = g.mulsq(g.sub(bi[3], br[3]))
-    n3i = g.mulsq(g.add(br[3], bi[3]))
+    # odd branch: c0 = b0; c1 = b1 * (1 - i)/sqrt2; c2 = b2 * (-i); c3 = b3 * (-1 - i)/sqrt2.  The factor 1 / sqrt2 of c1 and c3 is
+    # folded into the last stage (FOLD_SQ2): u1 = sqrt2 c1, u3 = sqrt2 c3 (with the sign convention n3i of the plain form)
+    u1r = g.add(br[1], bi[1])
+    u1i = g.sub(bi[1], br[1])
+    u3r = g.sub(bi[3], br[3])
+    m3i = g.add(br[3], bi[3])
 
     def dft4(s0r, s0i, s1r, s1i, s2r, s2i, dr, di):
         """outputs: y0 = s0 + s2, y2 = s0 - s2, y1 = s1 + (-i) d = (s1r + di, s1i - dr), y3 = (s1r - di, s1i + dr)"""
         return [(g.add(s0r, s2r), g.add(s0i, s2i)), (g.add(s1r, di), g.sub(s1i, dr)),
                 (g.sub(s0r, s2r), g.sub(s0i, s2i)), (g.sub(s1r, di), g.add(s1i, dr))]
 
+    def dft4_sq(s0r, s0i, s1r, s1i, s2r, s2i, dr, di):
+        """the same with s2 and d still carrying a factor sqrt2: eight packed FMAs with the constant +- 1 / sqrt2"""
+        return [(g.fmasq(s2r, s0r), g.fmasq(s2i, s0i)), (g.fmasq(di, s1r), g.fmasq(dr, s1i, True)),
+                (g.fmasq(s2r, s0r, True), g.fmasq(s2i, s0i, True)), (g.fmasq(di, s1r, True), g.fmasq(dr, s1i))]
+
     # even branch on a0..a3
     e = dft4(g.add(ar[0], ar[2]), g.add(ai[0], ai[2]), g.sub(ar[0], ar[2]), g.sub(ai[0], ai[2]),
              g.add(ar[1], ar[3]), g.add(ai[1], ai[3]), g.sub(ar[1], ar[3]), g.sub(ai[1], ai[3]))
-    # odd branch on c0..c3 with c2 = (b2i, -b2r), c3 = (c3r, -n3i)
+    # odd branch on c0..c3 with c2 = (b2i, -b2r), sqrt2 c1 = (u1r, u1i), sqrt2 c3 = (u3r, -m3i)
     s0r, s0i = g.add(br[0], bi[2]), g.sub(bi[0], br[2])      # c0 + c2
     s1r, s1i = g.sub(br[0], bi[2]), g.add(bi[0], br[2])      # c0 - c2
-    s2r, s2i = g.add(c1r, c3r), g.sub(c1i, n3i)              # c1 + c3
-    dr, di = g.sub(c1r, c3r), g.add(c1i, n3i)                # c1 - c3
-    o = dft4(s0r, s0i, s1r, s1i, s2r, s2i, dr, di)
+    s2r, s2i = g.add(u1r, u3r), g.sub(u1i, m3i)              # sqrt2 (c1 + c3)
+    dr, di = g.sub(u1r, u3r), g.add(u1i, m3i)                # sqrt2 (c1 - c3)
+    o = dft4_sq(s0r, s0i, s1r, s1i, s2r, s2i, dr, di)
     yr = [None] * 8
     yi = [None] * 8
     for q in range(4):
@@ -147,7 +158,7 @@ def main():
     out.append("inline cacfe_f2 cacfe_fma2(cacfe_f2 a, cacfe_f2 b, cacfe_f2 c) { return cacfe_f2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)}; }")
     out.append("#endif")
     out.append("CACFE_HD void cacfe_fft64x2(float (&re)[64], float (&im)[64]) {")
-    g.emit(f"const cacfe_f2 sq2 = cacfe_pk({SQ}, {SQ});")
+    g.emit(f"const cacfe_f2 sq2 = cacfe_pk({SQ}, {SQ}), nsq2 = cacfe_pk(-{SQ}, -{SQ});")
     # pass 1
     sr = {}  # (k1, b) -> scalar names after pass 1
     si = {}
