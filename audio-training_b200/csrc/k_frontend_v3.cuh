@@ -350,6 +350,29 @@ __global__ void __launch_bounds__(kVThreads, 1) stft_mel_v3_kernel(const Fronten
           win_c = t1.y;
           win_s = -t1.w;
         }
+#ifndef CACFE_K1_WIN_FULL   // A/B switch: compute all 64 window values per thread
+        if (WINC) {
+          // Hann: w[n + 2048] = 1 - w[n].  Thirty-two window values per thread (two FFMAs each), the other thirty-two products as
+          // x - x w: one packed FMA where the plain form has a packed multiply, and 64 scalar FFMAs fewer per frame pair.
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const int n = 64 * q + t64;
+            const cacfe_f2 wv = cacfe_pk(fmaf(kWinA[q], win_c, fmaf(kWinB[q], win_s, 0.5f)),
+                                         fmaf(kWinA[q + 1], win_c, fmaf(kWinB[q + 1], win_s, 0.5f)));
+            const cacfe_f2 xa = cacfe_mul2(cacfe_pk(fa[n], fa[n + 64]), wv), xb = cacfe_mul2(cacfe_pk(fb[n], fb[n + 64]), wv);
+            const cacfe_f2 ua = cacfe_pk(fa[n + 2048], fa[n + 2112]), ub = cacfe_pk(fb[n + 2048], fb[n + 2112]);
+            const cacfe_f2 ya = cacfe_sub2(ua, cacfe_mul2(ua, wv)), yb = cacfe_sub2(ub, cacfe_mul2(ub, wv));
+            re[q] = cacfe_lo(xa);
+            re[q + 1] = cacfe_hi(xa);
+            im[q] = cacfe_lo(xb);
+            im[q + 1] = cacfe_hi(xb);
+            re[q + 32] = cacfe_lo(ya);
+            re[q + 33] = cacfe_hi(ya);
+            im[q + 32] = cacfe_lo(yb);
+            im[q + 33] = cacfe_hi(yb);
+          }
+        } else
+#endif
 #pragma unroll
         for (int q = 0; q < 64; q += 2) {  // packed: the pair (q, q + 1) is also the input pair of cacfe_fft64x2
           const int n = 64 * q + t64;
