@@ -283,3 +283,28 @@ def test_keras_layer_adapter_keeps_the_reference_weights(golden):
     mag = L.MagTransform()
     assert [n for n, _ in mag._added] == ["a-power"] and float(mag._added[0][1][0]) == -1.0
     assert L.ExponentialMovingAverage(0.04, True).get_config() == {"coeff_init": 0.04, "trainable": True}
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line on stdout, the product arm's metric / unit / workload, the CPU
+    baseline it describes, and zero copy bytes.  Rank 1 of a torchrun launch prints nothing and exits 0."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
+    run = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [l for l in run.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    base = json.load(open(os.path.join(REPO, "BASELINE.json")))
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("clips/sec") and base["metric"].startswith("clips/sec")
+    assert "4096 clips" in line["config"]["workload"] and "sample" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] > 0
+    assert cb["value"] == max(cb["torch_port"], cb["numpy_port"])
+    assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert abs(line["ms_per_step"] * 1e-3 * line["value"] - 32) < 1e-6      # a step is one batch of 32 clips
+
+    other = subprocess.run(cmd, cwd=REPO, env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
+    assert other.returncode == 0 and other.stdout.strip() == ""
