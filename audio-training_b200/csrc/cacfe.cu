@@ -553,6 +553,14 @@ PcenGrid pcen_grid(long long rows_per_clip) {
   return g;
 }
 
+// One pass of the lane-per-row PCEN kernel.  Root 2 (the layer's initial value, tfpcen.py:78-87) takes the instantiation with
+// the root at compile time; cacfe_plan_force_generic(plan, 2) turns that off (tests: the two must agree bit for bit).
+template <int MODE>
+void pcen_pass(const cacfe_plan* p, dim3 grid, int block, int dyn, cudaStream_t st, const cacfe::PcenArgs& a) {
+  if (a.root_is_2 && !(p && p->no_hot)) cacfe::pcen_kernel<MODE, true><<<grid, block, dyn, st>>>(a);
+  else cacfe::pcen_kernel<MODE><<<grid, block, dyn, st>>>(a);
+}
+
 size_t pcen_ws_bytes(int B, long long rows_per_clip) {
   const PcenGrid g = pcen_grid(rows_per_clip);
   const size_t lanes = align256((size_t)B * g.gx * sizeof(float2));
@@ -986,11 +994,14 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
       cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
       cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
       cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_REDUCE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+      cudaFuncSetAttribute((const void*)cacfe::pcen_kernel<cacfe::PCEN_APPLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
     }
     return v;
   }();
   if (q->norm_scope == CACFE_NORM_NONE) {
-    cacfe::pcen_kernel<cacfe::PCEN_RAW><<<grid, g.block, dyn, st>>>(a);
+    pcen_pass<cacfe::PCEN_RAW>(p, grid, g.block, dyn, st, a);
     return check_launch(p, "pcen");
   }
   if (!ws) return fail(CACFE_EINVAL, "pcen: workspace required for the min-max scope");
@@ -999,12 +1010,12 @@ static int launch_pcen(cacfe_plan* p, const cacfe_pcen_params* q, const float* i
   a.partial = partial;
   a.extremes = extremes;
   a.per_clip_extremes = q->norm_scope == CACFE_NORM_CLIP;
-  cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<grid, g.block, dyn, st>>>(a);
+  pcen_pass<cacfe::PCEN_REDUCE>(p, grid, g.block, dyn, st, a);
   if (a.per_clip_extremes)
     cacfe::pcen_extremes_kernel<<<B, 256, 0, st>>>(partial, g.gx, extremes, a, 0);
   else
     cacfe::pcen_extremes_kernel<<<1, 256, 0, st>>>(partial, B * g.gx, extremes, a, 0);
-  cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<grid, g.block, dyn, st>>>(a);
+  pcen_pass<cacfe::PCEN_APPLY>(p, grid, g.block, dyn, st, a);
   return check_launch(p, "pcen", 3);
 }
 
@@ -1085,7 +1096,7 @@ int cacfe_pcen_backward(cacfe_plan* p, const cacfe_pcen_params* q, const float* 
     const int entries = q->norm_scope == CACFE_NORM_CLIP ? B : 1;
     const int per_entry = q->norm_scope == CACFE_NORM_CLIP ? g.gx : B * g.gx;
     a.f.partial = (float2*)(w + off[0]);
-    cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, B), g.block, 0, st>>>(a.f);
+    pcen_pass<cacfe::PCEN_REDUCE>(p, dim3(g.gx, B), g.block, 0, st, a.f);
     cacfe::pcen_extremes_kernel<<<entries, 256, 0, st>>>(a.f.partial, per_entry, extremes, a.f, 1);   // (mn, mx) of p
     cacfe::pcen_bwd_reduce_kernel<<<dim3(g.gx, B), g.block, 0, st>>>(a);
     cacfe::pcen_bwd_fold_kernel<<<entries, 32, 0, st>>>(partial, per_entry, extremes, fold);
@@ -1468,12 +1479,12 @@ static int hostpipe_run_impl(cacfe_hostpipe* h, const cacfe_pcen_params* q, cons
     ac.partial = h->d_partial + (size_t)b0 * g.gx;
     ac.extremes = h->d_extremes + b0;
     if (q->norm_scope == CACFE_NORM_NONE) {
-      cacfe::pcen_kernel<cacfe::PCEN_RAW><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      pcen_pass<cacfe::PCEN_RAW>(p, dim3(g.gx, nb), g.block, 0, st, ac);
     } else {
-      cacfe::pcen_kernel<cacfe::PCEN_REDUCE><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      pcen_pass<cacfe::PCEN_REDUCE>(p, dim3(g.gx, nb), g.block, 0, st, ac);
       if (!global) {
         cacfe::pcen_extremes_kernel<<<nb, 256, 0, st>>>(ac.partial, g.gx, h->d_extremes + b0, ac, 0);
-        cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+        pcen_pass<cacfe::PCEN_APPLY>(p, dim3(g.gx, nb), g.block, 0, st, ac);
       }
     }
     if ((rc = check_launch(p, "hostpipe", global ? 1 : (q->norm_scope == CACFE_NORM_NONE ? 1 : 3))) != CACFE_OK) return rc;
@@ -1502,7 +1513,7 @@ static int hostpipe_run_impl(cacfe_hostpipe* h, const cacfe_pcen_params* q, cons
       ac.out = h->d_out[s];
       ac.extremes = h->d_extremes;
       ac.per_clip_extremes = 0;
-      cacfe::pcen_kernel<cacfe::PCEN_APPLY><<<dim3(g.gx, nb), g.block, 0, st>>>(ac);
+      pcen_pass<cacfe::PCEN_APPLY>(p, dim3(g.gx, nb), g.block, 0, st, ac);
       if ((rc = check_launch(p, "hostpipe")) != CACFE_OK) return rc;
       CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)b0 * clip, h->d_out[s], (size_t)nb * clip * sizeof(float),
                                cudaMemcpyDeviceToHost, st));

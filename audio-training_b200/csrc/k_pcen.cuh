@@ -32,22 +32,47 @@ struct PcenArgs {
   const float2* extremes;        // [1] or [B] (min, max)    (APPLY)
   int per_clip_extremes;
   const float* init;             // ema_kernel: initial state [outer][inner], or nullptr = inputs[:, 0, :]
+  int zero;                      // always 0, and only the host knows: pcen_kernel's load fence
 };
 
 enum : int { PCEN_REDUCE = 0, PCEN_APPLY = 1, PCEN_RAW = 2 };
 
+// MUFU wrappers in their flush-to-zero form: one instruction each.  The default forms (`__log2f`, `exp2f`, `rsqrtf` without
+// -ftz) wrap the same MUFU in a compare and two predicated multiplies that rescale subnormal arguments / results -- nine
+// instructions per element of a pass that issue, not HBM, holds back (APPLY: 36 instructions per element, issue slots 68 %).
+// For normal arguments and results the values are the same bit for bit.  Subnormals: eps + M subnormal needs M = -eps to
+// 1e-38 (impossible for eps = 1e-6: the sum of two floats of opposite sign is a multiple of 9e-14); a smoother gain below
+// 1e-38 needs M > 1e38; a subnormal y is mapped to 0 by the select in pcen_root (error <= 1.1e-19).
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // y = x / (eps + M)^gain + bias,  with  x / (eps + M)^gain == x * 2^(-gain * log2(eps + M))      (MUFU lg2 / ex2)
 __device__ __forceinline__ float pcen_y(float x, float m, const PcenArgs& a) {
-  const float smooth = exp2f(-a.gain * __log2f(a.eps + m));
+  const float smooth = ex2_ftz(-a.gain * lg2_ftz(a.eps + m));
   return fmaf(x, smooth, a.bias);
 }
 // y^(1/root) - bias^(1/root).  root 2 (the layer's initial value): y * rsqrt(y) -- one MUFU and one multiply, <= 2 ulp --
-// instead of the IEEE sqrt sequence
+// instead of the IEEE sqrt sequence.  ROOT2: the caller knows at compile time that root is 2 (no branch per element).
+template <bool ROOT2 = false>
 __device__ __forceinline__ float pcen_root(float y, const PcenArgs& a) {
-  const float r = a.root_is_2 ? (y > 0.0f ? y * rsqrtf(y) : 0.0f) : exp2f(a.inv_root * __log2f(y));
+  const float r = (ROOT2 || a.root_is_2) ? (y >= 1.17549435e-38f ? y * rsqrt_ftz(y) : 0.0f) : ex2_ftz(a.inv_root * lg2_ftz(y));
   return r - a.bias_pow;
 }
-__device__ __forceinline__ float pcen_point(float x, float m, const PcenArgs& a) { return pcen_root(pcen_y(x, m, a), a); }
+template <bool ROOT2 = false>
+__device__ __forceinline__ float pcen_point(float x, float m, const PcenArgs& a) { return pcen_root<ROOT2>(pcen_y(x, m, a), a); }
 
 // Loads in flight per lane.  Measured on [4096, 513, 160], both passes of the tensor-global scope (tools/probe_pcen_waves.py,
 // results bit-identical): 8 -> 0.811 ms, 12 -> 0.821, 16 -> 0.778, 24 -> 0.776, 32 -> 0.752, 48 -> 0.868, 64 -> 0.895.  The passes are latency-bound
@@ -59,9 +84,14 @@ __device__ __forceinline__ float pcen_point(float x, float m, const PcenArgs& a)
 constexpr int kPcenUnroll = CACFE_PCEN_UNROLL;
 constexpr int kEmaUnroll = 8;
 
-template <int MODE>
+// ROOT2: the layer's initial root (2) resolved at compile time -- no branch per element.
+#ifndef CACFE_PCEN_FENCE       // A/B switch (tools/probe_pcen_hot.py)
+#define CACFE_PCEN_FENCE 1
+#endif
+template <int MODE, bool ROOT2 = false>
 __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
   __shared__ float scratch[64];
+  const int inner = a.inner;
   // REDUCE walks the clips from the last to the first and APPLY from the first to the last: what the producer wrote last (and
   // what REDUCE read last) is still in the 126 MB L2 when the next pass starts there
   const int clip = MODE == PCEN_REDUCE ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
@@ -69,8 +99,8 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
   const bool live = r < a.rows_per_clip;
   float mn = INFINITY, mx = -INFINITY;
   if (live) {
-    const int o = r / a.inner, i = r - o * a.inner;
-    const size_t base = ((size_t)clip * (a.rows_per_clip / a.inner) + o) * a.T * a.inner + i;
+    const int o = r / inner, i = r - o * inner;
+    const size_t base = ((size_t)clip * (a.rows_per_clip / inner) + o) * a.T * inner + i;
     const float* x = a.in + base;
     float* y = a.out + base;
     float scale = 1.0f, shift = 0.0f;
@@ -83,7 +113,7 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
       shift = e.y;                                                                  // reaches 1 and is clamped to it
     }
     float m = x[0];  // initial state = inputs[:, 0, :]  (tfpcen.py:92)
-    auto point = [&](float v, int t) {
+    auto point = [&](float v, float* dst) {
       m = __fadd_rn(__fmul_rn(a.w, v), __fmul_rn(a.one_minus_w, m));  // unfused, the reference's f32 order
       if (MODE == PCEN_REDUCE) {
         // the root is monotone: the extremes of p are the roots of the extremes of y (pcen_extremes_kernel takes them with
@@ -92,10 +122,10 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
         mn = min_nan(mn, yy);   // NaN-propagating like tf.reduce_min / reduce_max (tfpcen.py:108-109)
         mx = max_nan(mx, yy);
       } else {
-        float p = pcen_point(v, m, a);
+        float p = pcen_point<ROOT2>(v, m, a);
         // clamp to [-1, 1] with NaN passing through: a constant tensor (range 0 -> 0 * inf) gives NaN as the reference's 0 / 0 does
         if (MODE == PCEN_APPLY) p = max_nan(min_nan(fmaf(p - shift, scale, -1.0f), 1.0f), -1.0f);
-        y[(size_t)t * a.inner] = p;
+        *dst = p;
       }
     };
     // (prefetching the next batch into a second register set -- what ema_kernel does -- costs this MUFU-bound kernel
@@ -104,11 +134,18 @@ __global__ void __launch_bounds__(256) pcen_kernel(const PcenArgs a) {
     for (; t + kPcenUnroll <= a.T; t += kPcenUnroll) {
       float v[kPcenUnroll];
 #pragma unroll
-      for (int u = 0; u < kPcenUnroll; ++u) v[u] = ld_stream(x + (size_t)(t + u) * a.inner);
+      for (int u = 0; u < kPcenUnroll; ++u) v[u] = ld_stream(x + (size_t)(t + u) * inner);
+      // load fence: the first value is made to depend on the last load (OR with `last & 0`, the zero read from the constant
+      // bank).  Without it ptxas sinks the loads below the arithmetic to save registers (32 instead of 48 - 60) and about nine
+      // of the 32 stay in flight: measured on [4096, 513, 160], REDUCE + APPLY, 0.731 ms without and 0.713 ms with the fence.
+      // (Compile-time row stride, immediate offsets: four instructions fewer per element, and ptxas hoists the one load the
+      // fence names; with a fence over all 32 loads 0.710 ms -- once the loads are in flight the instruction count is not what
+      // bounds the pass.)
+      if (CACFE_PCEN_FENCE) v[0] = __int_as_float(__float_as_int(v[0]) | (__float_as_int(v[kPcenUnroll - 1]) & a.zero));
 #pragma unroll
-      for (int u = 0; u < kPcenUnroll; ++u) point(v[u], t + u);
+      for (int u = 0; u < kPcenUnroll; ++u) point(v[u], y + (size_t)(t + u) * inner);
     }
-    for (; t < a.T; ++t) point(ld_stream(x + (size_t)t * a.inner), t);
+    for (; t < a.T; ++t) point(ld_stream(x + (size_t)t * inner), y + (size_t)t * inner);
   }
   if (MODE == PCEN_REDUCE) {
     block_minmax_nan(mn, mx, scratch);

@@ -241,6 +241,25 @@ def test_k1_specialisations_bit_identical(oracle):
     assert torch.equal(hot.stft(x), plain.stft(x))
 
 
+def test_pcen_root2_instantiation_bit_identical():
+    """The lane-per-row PCEN kernel resolves root == 2 (the layer's initial value) at compile time; the plain instantiation
+    (force_generic(2)) must give the same bits, for every scope, and also on subnormal / zero / huge inputs where the
+    flush-to-zero MUFU forms could differ from each other if the two paths did not share them."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((6, 513, 160), device="cuda", generator=g) ** 4 * 50.0
+    x[0, 100:110, 5] = 0.0
+    x[1, :, 7] = 1e-42          # subnormal band
+    x[2, 200:, 9] = 3e37
+    hot, plain = rt.Plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0), \
+        rt.Plan(rt.FrontendConfig(normalize=True, channels=1, out_layout="btm"), 0)
+    plain.force_generic(2)
+    for scope in ("tensor", "clip", "none"):
+        p = rt.pcen_params(norm_scope=scope)
+        a, b = hot.pcen(x, p), plain.pcen(x, p)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), scope
+        assert torch.isfinite(a).all(), scope
+
+
 def test_k1_jitter():
     """Stand-in for racecheck (compute-sanitizer is closed on this pool): libcacfe_jitter.so is the same library built with
     -DCACFE_K1_JITTER, which puts a pseudo-random pause of 0..2 us before every hand-over operation of the persistent fused
