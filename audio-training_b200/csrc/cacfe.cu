@@ -594,6 +594,7 @@ int fill_pcen_args(const cacfe_pcen_params* q, cacfe::PcenArgs& a) {
   const float w = fminf(fmaxf(q->smooth, 0.0f), 1.0f);        // tf.clip_by_value(smooth, 0, 1)   tfpcen.py:35
   const float gain = fminf(q->gain, 1.0f);                     // tfpcen.py:90
   const float root = fmaxf(q->root, 1.0f);                     // tfpcen.py:91
+  a.zero = 0;
   a.w = w;
   a.one_minus_w = 1.0f - w;
   a.gain = gain;

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(256) ema_kernel(const PcenArgs a) {
   // tf.scan's initializer (tfpcen.py:36-38): any state; the reference's only caller passes inputs[:, 0, :] (tfpcen.py:92)
   float m = a.init != nullptr ? a.init[((size_t)clip * (a.rows_per_clip / a.inner) + o) * a.inner + i] : x[0];
   int t = 0;
+#ifdef CACFE_EMA_DOUBLE_BUFFER   // A/B switch: the round-1 form, a double-buffered batch of 8 (16 loads in flight)
   float v[kEmaUnroll], nv[kEmaUnroll];
   if (a.T >= kEmaUnroll) {
 #pragma unroll
@@ -217,6 +218,20 @@ __global__ void __launch_bounds__(256) ema_kernel(const PcenArgs a) {
 #pragma unroll
     for (int u = 0; u < kEmaUnroll; ++u) v[u] = nv[u];
   }
+#else
+  // batches of 32 loads held ahead of the arithmetic by the same fence as in pcen_kernel
+  for (; t + kPcenUnroll <= a.T; t += kPcenUnroll) {
+    float v[kPcenUnroll];
+#pragma unroll
+    for (int u = 0; u < kPcenUnroll; ++u) v[u] = ld_stream(x + (size_t)(t + u) * a.inner);
+    v[0] = __int_as_float(__float_as_int(v[0]) | (__float_as_int(v[kPcenUnroll - 1]) & a.zero));
+#pragma unroll
+    for (int u = 0; u < kPcenUnroll; ++u) {
+      m = __fadd_rn(__fmul_rn(a.w, v[u]), __fmul_rn(a.one_minus_w, m));  // w*x + (1-w)*a, unfused like TF
+      y[(size_t)(t + u) * a.inner] = m;
+    }
+  }
+#endif
   for (; t < a.T; ++t) {
     m = __fadd_rn(__fmul_rn(a.w, x[(size_t)t * a.inner]), __fmul_rn(a.one_minus_w, m));
     y[(size_t)t * a.inner] = m;
