@@ -132,7 +132,8 @@ long long cacfe_plan_launch_count(const cacfe_plan* plan);
 int cacfe_plan_profile(cacfe_plan* plan, int enable);
 /* enable == 1: use the generic (non-TMA, one CTA per tile) form of the fused kernel even where the streaming form
  * applies; both compute the same features (parity tests exercise both).  enable == 2: the streaming kernel without its
- * compile-time specialisations of the common configurations (bit-identical results; tests).  0: default. */
+ * compile-time specialisations of the common configurations, and the PCEN passes without their root-2 instantiation
+ * (bit-identical results; tests).  0: default. */
 int cacfe_plan_force_generic(cacfe_plan* plan, int enable);
 int cacfe_plan_profile_read(cacfe_plan* plan, double* k1_ms, long long* k1_launches);
 
