@@ -188,6 +188,25 @@ def test_sine_bin_centre(oracle):
     assert z[10, k0 + 5] < 1e-7
 
 
+def test_normalisation_is_a_scale_on_frames_inside_the_clip(oracle):
+    """Linearity of the path: the clip normalisation is affine, and the Hann-windowed DFT of a constant
+    lives in bins 0 and +-1, which the bank (bins >= 5) never reads -- so on the 498 frames that lie inside the clip the mel power
+    of the normalised clip is (2 / range)^2 times that of the raw clip.  The 15 frames that reach into the padding (zero AFTER
+    normalisation) do not obey it."""
+    x = oracle.synth_clips(np.arange(4))
+    w = oracle.mel_f(48000, 160, 100, 11000, 4096, 1000)
+    truth = oracle.raw_to_mel(oracle.normalize(x, np.float32), w, channels=0, dtype=np.float64)      # [B, M, T]
+    raw = oracle.raw_to_mel(x, w, channels=0, dtype=np.float32).astype(np.float64)
+    rng = (x - x.min(axis=1, keepdims=True)).max(axis=1, keepdims=True).astype(np.float64)
+    scaled = raw * (2.0 / rng)[:, :, None] ** 2
+    inside = oracle.num_frames_tf(144000, 4096, 281, False)
+    assert inside == 498
+    ok, worst = oracle.within_tolerance(scaled[:, :, :inside].astype(np.float32), truth[:, :, :inside])
+    assert ok and worst < 0.2, worst
+    ok, _ = oracle.within_tolerance(scaled[:, :, inside:].astype(np.float32), truth[:, :, inside:])
+    assert not ok
+
+
 def test_ema_closed_forms(oracle):
     const = np.full((1, 50, 3), 2.5)
     assert np.allclose(oracle.ema(const), 2.5)
